@@ -1,0 +1,184 @@
+/*
+ * sofima_b200 -- C ABI of the B200 (sm_100a) backend for SOFIMA's two hot paths.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point names the reference interface it replaces (file:line under
+ * google-research/sofima @ efd7fd6).  All array pointers are DEVICE pointers on
+ * the context's device unless a parameter says "host"; all work is enqueued on
+ * the context's stream.  Return value: 0 = OK, otherwise a SOFIMA_E* code and
+ * sofima_last_error() holds a message.
+ *
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef SOFIMA_B200_H_
+#define SOFIMA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOFIMA_B200_ABI_VERSION 1
+
+enum {
+  SOFIMA_OK = 0,
+  SOFIMA_EINVAL = 1,       /* bad argument (maps to ValueError / AssertionError) */
+  SOFIMA_EUNSUPPORTED = 2, /* valid in the reference, not built yet (NotImplementedError) */
+  SOFIMA_ECUDA = 3,        /* CUDA runtime error (RuntimeError) */
+  SOFIMA_ENOMEM = 4
+};
+
+typedef struct sofima_ctx sofima_ctx;
+
+/* Context = device + stream + cached scratch memory.  `stream` is a cudaStream_t
+ * (NULL = legacy default stream).  One context per host thread. */
+int sofima_ctx_create(int device, void* stream, sofima_ctx** out);
+int sofima_ctx_destroy(sofima_ctx* ctx);
+int sofima_ctx_set_stream(sofima_ctx* ctx, void* stream);
+const char* sofima_last_error(const sofima_ctx* ctx); /* ctx may be NULL */
+int sofima_abi_version(void);
+/* Number of kernel launches issued through `ctx` so far (bench "gpu_launches"). */
+int64_t sofima_ctx_launch_count(const sofima_ctx* ctx);
+
+/* ------------------------------------------------------------------------- *
+ *  Mesh relaxation  (reference: mesh.py)
+ * ------------------------------------------------------------------------- */
+
+/* Mirror of mesh.IntegrationConfig (mesh.py:282-338).  Doubles, because the
+ * reference folds Python-float constants in double before rounding to fp32. */
+typedef struct {
+  double dt, gamma, k0, k;
+  double stride[3]; /* xy[z]; stride[2] ignored for 2-d */
+  int32_t num_iters;
+  int32_t fire;
+  double f_alpha, f_inc, f_dec, alpha;
+  int32_t n_min;
+  double dt_max;
+  double start_cap, final_cap, cap_scale;
+  int32_t cap_upscale_every;
+  int32_t prefer_orig_order;
+  int32_t remove_drift;
+} sofima_integration_config;
+
+enum {
+  SOFIMA_FORCE_INPLANE = 0, /* mesh.inplane_force   (mesh.py:42-169)  */
+  SOFIMA_FORCE_MESH3D = 1   /* mesh.elastic_mesh_3d (mesh.py:192-279) */
+};
+
+/* Mesh arrays are fp32, component-major: [ncomp][nb][nz][ny][nx] contiguous, with
+ * ncomp = 2 (in-plane; the reference's [2, z, y, x] has nb = z, nz = 1) or 3
+ * ([3, batch.., z, y, x] has nb = prod(batch)). */
+typedef struct {
+  int32_t ncomp;
+  int64_t nb, nz, ny, nx;
+} sofima_mesh_shape;
+
+/* Replaces mesh.inplane_force / mesh.elastic_mesh_3d called on their own
+ * (mesh.py:42, :192).  out = internal spring force field of x. */
+int sofima_mesh_force(sofima_ctx* ctx, int force_kind, const float* x,
+                      const sofima_mesh_shape* shape, double k,
+                      const double* stride, int prefer_orig_order, float* out);
+
+/* Same with the `links` argument of elastic_mesh_3d (mesh.py:197): links_xyz is a
+ * HOST array [nlinks][3] of xyz directions in {-1,0,1}; NULL = MESH_LINK_DIRECTIONS. */
+int sofima_mesh_force_links(sofima_ctx* ctx, int force_kind, const float* x,
+                            const sofima_mesh_shape* shape, double k,
+                            const double* stride, int prefer_orig_order,
+                            const int32_t* links_xyz, int nlinks, float* out);
+
+/* Replaces ONE call of mesh.velocity_verlet (mesh.py:371-521) plus the two
+ * reductions relax_mesh does on its result (mesh.py:584-586).
+ *   x, v       in/out, updated in place
+ *   a          out (acceleration at the final x), may not be NULL
+ *   prev       may be NULL (no inter-section springs)
+ *   dt, alpha, cap   host pointers, in: fire_dt / fire_alpha / force_cap,
+ *                    out: their values after the chunk (FIRE only)
+ *   n_pos      host, out (FIRE only; -1 otherwise)
+ *   e_kin      host, out: sum |v|^2      v_max: host, out: max |v|
+ * Blocks until the chunk has finished (the reference blocks here too,
+ * mesh.py:585). */
+int sofima_mesh_chunk(sofima_ctx* ctx, int force_kind, float* x, float* v,
+                      float* a, const float* prev,
+                      const sofima_mesh_shape* shape,
+                      const sofima_integration_config* cfg, float* dt,
+                      float* alpha, float* cap, int32_t* n_pos, double* e_kin,
+                      float* v_max);
+
+/* Device-side solver state; also the layout of the read-back block. */
+typedef struct {
+  float dt, alpha, cap, gate; /* FIRE scalars after the last step; gate = (power >= 0) */
+  int32_t n_pos;
+  uint32_t ticket;            /* internal */
+  float mean_x[3], mean_v[3]; /* remove_drift means of the last step */
+  double power;               /* vdot(a, v) of the last step (mesh.py:455) */
+  double e_kin;               /* sum |v|^2  (mesh.py:585) */
+  float v_max;                /* max |v|    (mesh.py:586) */
+  int32_t pad;
+} sofima_mesh_state;
+
+/* Same, without the final synchronisation: a sofima_mesh_state is copied to the
+ * pinned host block `results_pinned` when the stream reaches that point.  Used to
+ * queue many chunks back to back. */
+int sofima_mesh_chunk_async(sofima_ctx* ctx, int force_kind, float* x, float* v,
+                            float* a, const float* prev,
+                            const sofima_mesh_shape* shape,
+                            const sofima_integration_config* cfg, float dt,
+                            float alpha, float cap,
+                            sofima_mesh_state* results_pinned);
+
+/* ------------------------------------------------------------------------- *
+ *  Patch flow  (reference: flow_field.py)
+ * ------------------------------------------------------------------------- */
+
+enum { SOFIMA_U8 = 0, SOFIMA_F32 = 1 };
+
+typedef struct {
+  int32_t ndim;            /* 2 or 3 */
+  int32_t img_dtype;       /* SOFIMA_U8 | SOFIMA_F32 (both images) */
+  int64_t pre_shape[3];    /* [[z,] y, x], leading entries first */
+  int64_t post_shape[3];
+  int64_t pre_mask_shape[3];  /* masks may be larger than the images */
+  int64_t post_mask_shape[3];
+  int32_t pre_patch[3];
+  int32_t post_patch[3];
+  int32_t has_mean;        /* 0: per-patch (masked) mean, 1: use `mean` */
+  float mean;
+  int32_t min_distance;    /* peak_min_distance, scalar (flow_field.py:235) */
+  float threshold_rel;     /* 0.5 in the reference (flow_field.py:394) */
+  int32_t peak_radius[3];
+} sofima_xcorr_params;
+
+/* Replaces flow_field.batched_xcorr_peaks (flow_field.py:385-441) for one batch:
+ * gathers `batch` patch pairs at pre_starts / post_starts ([batch, ndim] int32,
+ * [[z,] y, x] order), cross-correlates them (masked_xcorr, flow_field.py:36-156),
+ * finds the two highest peaks with the reference's batch-coupled rule
+ * (flow_field.py:259-268) and writes out_peaks[batch, ndim+2] =
+ * (x, y[, z], sharpness, ratio).  Masks are uint8 (0/1) or NULL. */
+int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p,
+                       const void* pre_img, const void* post_img,
+                       const uint8_t* pre_mask, const uint8_t* post_mask,
+                       const int32_t* pre_starts, const int32_t* post_starts,
+                       int64_t batch, float* out_peaks);
+
+/* Test hook: the raw correlation images of one batch, [batch, prod(pre+post-1)]
+ * fp32 (what _batched_xcorr returns, flow_field.py:278-371). */
+int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p,
+                        const void* pre_img, const void* post_img,
+                        const uint8_t* pre_mask, const uint8_t* post_mask,
+                        const int32_t* pre_starts, const int32_t* post_starts,
+                        int64_t batch, float* out_xcorr);
+
+/* Replaces flow_field._batched_peaks (flow_field.py:205-275) on caller-supplied
+ * correlation images img[batch, [z,] y, x] (the LICONN notebook calls it
+ * directly).  center_offset in [[z,] y, x] order. */
+int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img,
+                         const int64_t* img_shape, int64_t batch,
+                         const int32_t* center_offset, int min_distance,
+                         float threshold_rel, const int32_t* peak_radius,
+                         float* out_peaks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFIMA_B200_H_ */

@@ -1,0 +1,101 @@
+// Shared plumbing of the sofima_b200 C-ABI library: context, error reporting,
+// scratch memory, launch accounting.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../include/sofima_b200.h"
+
+struct sofima_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  int64_t launches = 0;
+  char err[512] = {0};
+  // Named scratch buffers that only ever grow; freed with the context.
+  struct Buf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+  };
+  std::map<std::string, Buf> scratch;
+  void* pinned = nullptr;  // small pinned host block for scalar read-back
+  size_t pinned_bytes = 0;
+};
+
+namespace sofima {
+
+extern thread_local char g_last_error[512];
+
+inline int fail(sofima_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) strncpy(ctx->err, buf, sizeof(ctx->err) - 1);
+  strncpy(g_last_error, buf, sizeof(g_last_error) - 1);
+  return code;
+}
+
+#define SOFIMA_CUDA(ctx, expr)                                                   \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess)                                                       \
+      return sofima::fail((ctx), SOFIMA_ECUDA, "%s:%d: %s -> %s", __FILE__,     \
+                          __LINE__, #expr, cudaGetErrorString(_e));              \
+  } while (0)
+
+#define SOFIMA_CHECK_LAUNCH(ctx)                                                 \
+  do {                                                                           \
+    (ctx)->launches++;                                                           \
+    SOFIMA_CUDA((ctx), cudaGetLastError());                                      \
+  } while (0)
+
+// Returns a device scratch buffer of at least `bytes` under `name` (grow-only).
+inline int scratch(sofima_ctx* ctx, const char* name, size_t bytes, void** out) {
+  auto& b = ctx->scratch[name];
+  if (b.bytes < bytes) {
+    if (b.ptr) {
+      SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      SOFIMA_CUDA(ctx, cudaFree(b.ptr));
+      b.ptr = nullptr;
+      b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+      b.ptr = nullptr;
+      return fail(ctx, SOFIMA_ENOMEM, "cudaMalloc(%zu) for scratch '%s': %s", want,
+                  name, cudaGetErrorString(e));
+    }
+    b.bytes = want;
+  }
+  *out = b.ptr;
+  return SOFIMA_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+}  // namespace sofima

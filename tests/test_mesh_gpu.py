@@ -1,0 +1,238 @@
+"""GPU parity tests: sofima_b200.mesh (CUDA, through the C ABI) vs the oracle and
+the golden vectors generated from the reference source.
+
+Tolerance: north_star asks for 1e-5 abs on node positions.  The kernels are
+bit-faithful to the fp32 reference arithmetic, so most comparisons are exact;
+where a global reduction order enters (remove_drift means) 2e-6 is allowed.
+"""
+
+import ast
+
+import numpy as np
+import pytest
+
+from oracle import mesh_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-5  # north_star tolerance on node positions
+
+
+@pytest.fixture(scope='module')
+def mesh():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  from sofima_b200 import mesh as m
+  return m
+
+
+def _cfg(mesh, golden, tag):
+  return mesh.IntegrationConfig(**ast.literal_eval(str(golden[f'{tag}_cfg'])))
+
+
+# ---- ports of /root/reference/tests/mesh_test.py, run on the CUDA path -----------
+
+
+def _kat_x():
+  x = np.zeros((2, 1, 50, 50))
+  x[0, 0, 20:30, 10] = 3
+  x[0, 0, 20:30, 40] = -4
+  x[1, 0, 30, 10:20] = 2
+  return x
+
+
+def test_relaxation_fire(mesh, mesh_golden):
+  cfg = mesh.IntegrationConfig(dt=0.01, gamma=0.0, k0=0.1, k=0.1, stride=(10, 10),
+                               num_iters=100, max_iters=10000, stop_v_max=0.001,
+                               fire=True)
+  x = _kat_x()
+  new_x, e_kin, t = mesh.relax_mesh(x, np.zeros_like(x), cfg)
+  np.testing.assert_array_almost_equal(new_x, np.zeros_like(x), decimal=3)
+  assert t == int(mesh_golden['kat_fire_t'])
+  np.testing.assert_allclose(new_x, mesh_golden['kat_fire_x'], rtol=0, atol=ATOL)
+  np.testing.assert_allclose(e_kin, mesh_golden['kat_fire_ekin'], rtol=1e-4)
+
+
+def test_relaxation_damped(mesh, mesh_golden):
+  cfg = mesh.IntegrationConfig(dt=0.01, gamma=0.9 * np.sqrt(4 * 0.1), k0=0.1,
+                               k=0.1, stride=(10, 10), num_iters=100,
+                               max_iters=10000, stop_v_max=0.001, fire=False)
+  x = _kat_x()
+  new_x, e_kin, t = mesh.relax_mesh(x, np.zeros_like(x), cfg)
+  np.testing.assert_array_almost_equal(new_x, np.zeros_like(x), decimal=3)
+  assert t == int(mesh_golden['kat_damped_t'])
+  np.testing.assert_allclose(new_x, mesh_golden['kat_damped_x'], rtol=0, atol=ATOL)
+
+
+def test_equilibrium(mesh):
+  x = np.zeros((2, 1, 10, 10))
+  np.testing.assert_array_equal(x, mesh.inplane_force(x, k=1.0, stride=(40.0, 40.0)))
+  x = np.zeros((3, 10, 10, 10))
+  np.testing.assert_array_equal(x, mesh.elastic_mesh_3d(x, k=1.0, stride=40.0))
+  x = np.zeros((3, 5, 10, 10, 10))
+  np.testing.assert_array_equal(x, mesh.elastic_mesh_3d(x, k=1.0, stride=40.0))
+
+
+def test_force_closed_form(mesh):
+  x = np.zeros((2, 1, 10, 10))
+  dx, dy, k, l0 = 4, -3, 0.1, 10.0
+  x[0, 0, 5, 5], x[1, 0, 5, 5] = dx, dy
+  f = mesh.inplane_force(x, k=k, stride=(l0, 10))
+  l = np.sqrt((l0 + dx) ** 2 + dy**2)
+  np.testing.assert_allclose(
+      [k * (l - l0) * (l0 + dx) / l, k * (l - l0) * dy / l], f[:, 0, 5, 4],
+      rtol=1e-6)
+  l = np.sqrt(dx**2 + (l0 + dy) ** 2)
+  np.testing.assert_allclose(
+      [k * (l - l0) * dx / l, k * (l - l0) * (l0 + dy) / l], f[:, 0, 4, 5],
+      rtol=1e-6)
+  l2, k2 = l0 * np.sqrt(2.0), k / np.sqrt(2.0)
+  l = np.sqrt((l0 - dx) ** 2 + (l0 - dy) ** 2)
+  np.testing.assert_allclose(
+      [-k2 * (l - l2) * (l0 - dx) / l, -k2 * (l - l2) * (l0 - dy) / l],
+      f[:, 0, 6, 6], rtol=1e-5)
+  l = np.sqrt((l0 + dx) ** 2 + (l0 - dy) ** 2)
+  np.testing.assert_allclose(
+      [k2 * (l - l2) * (l0 + dx) / l, -k2 * (l - l2) * (l0 - dy) / l],
+      f[:, 0, 6, 4], rtol=1e-5)
+
+
+def test_2d_3d_consistency(mesh):
+  planar = ((1, 0, 0), (0, 1, 0), (1, 1, 0), (-1, 1, 0))
+  x = np.random.default_rng(42).random((3, 1, 50, 50))
+  x[2] = 0.0
+  for poo in (False, True):
+    f2 = mesh.inplane_force(x[:2], 0.01, (40.0, 40.0), poo)
+    f3 = mesh.elastic_mesh_3d(x, 0.01, (40.0, 40.0, 14.0), poo, links=planar)
+    np.testing.assert_allclose(f2[:2], f3[:2], atol=1e-5)
+
+
+def test_errors(mesh):
+  base = dict(dt=0.01, gamma=0.0, k0=0.1, k=0.1, stride=(10, 10), num_iters=10,
+              max_iters=10, stop_v_max=0.1)
+  x = np.zeros((2, 1, 4, 4))
+  with pytest.raises(NotImplementedError):
+    mesh.relax_mesh(x, x, mesh.IntegrationConfig(**base, fire=False, start_cap=1.0))
+  with pytest.raises(ValueError):
+    mesh.relax_mesh(x, x, mesh.IntegrationConfig(**base, start_cap=1.0,
+                                                  cap_scale=1.0))
+  with pytest.raises(ValueError):
+    mesh.relax_mesh(x, x, mesh.IntegrationConfig(**base), prev_fn=lambda a: a)
+  with pytest.raises(ValueError):
+    mesh.inplane_force(x, 0.1, (1, 2, 3))
+  with pytest.raises(NotImplementedError):
+    mesh.relax_mesh(x, x, mesh.IntegrationConfig(**base), mesh_force=lambda *a: 0)
+
+
+# ---- golden vectors produced by the reference's own mesh.py -----------------------
+
+
+@pytest.mark.parametrize('poo', [0, 1])
+def test_golden_forces(mesh, mesh_golden, poo):
+  f = mesh.inplane_force(mesh_golden['force2d_x'], 0.1, (40.0, 30.0), bool(poo))
+  np.testing.assert_array_equal(f, mesh_golden[f'force2d_poo{poo}'])
+  f = mesh.elastic_mesh_3d(mesh_golden['force3d_x'], 0.1, (40.0, 40.0, 14.0),
+                           bool(poo))
+  np.testing.assert_array_equal(f, mesh_golden[f'force3d_poo{poo}'])
+
+
+@pytest.mark.parametrize(
+    'tag', ['fire_poo', 'fire_cap', 'fire_drift', 'damped', 'fire_nan_x', 'fire_3d'])
+def test_golden_chunks(mesh, mesh_golden, tag):
+  g = mesh_golden
+  cfg = _cfg(mesh, g, tag)
+  force = mesh.elastic_mesh_3d if tag.endswith('3d') else mesh.inplane_force
+  x = g[f'{tag}_x0']
+  v = np.zeros_like(x)
+  prev = g[f'{tag}_prev'] if f'{tag}_prev' in g.files else None
+  dt, alpha, cap = cfg.dt, cfg.alpha, cfg.start_cap
+  for i in range(g[f'{tag}_xs'].shape[0]):
+    st = mesh.velocity_verlet(x, v, prev, cfg, cap, dt, alpha, mesh_force=force)
+    x, v = st[:2]
+    if cfg.fire:
+      dt, alpha, n_pos, cap = st[-4:]
+      np.testing.assert_allclose([dt, alpha, n_pos, cap], g[f'{tag}_scalars'][i],
+                                 rtol=1e-6)
+    tol = 1e-5 if cfg.remove_drift else 0.0
+    np.testing.assert_allclose(x, g[f'{tag}_xs'][i], rtol=0, atol=tol)
+    np.testing.assert_allclose(v, g[f'{tag}_vs'][i], rtol=0, atol=tol)
+
+
+# ---- seeded oracle comparisons at sizes the oracle finishes in seconds ------------
+
+
+@pytest.mark.parametrize('shape,poo,k0', [
+    ((2, 1, 97, 131), True, 0.1),     # ragged against the 32x32 tiles
+    ((2, 3, 64, 64), False, 0.05),
+    ((2, 2, 1, 70), True, 0.1),       # degenerate: a single row
+    ((2, 1, 33, 1), False, 0.1),      # degenerate: a single column
+])
+def test_oracle_trajectory(mesh, shape, poo, k0):
+  import scipy.ndimage as ndi
+  rng = np.random.default_rng(5)
+  prev = (ndi.gaussian_filter(rng.standard_normal(shape), (0, 0, 3, 3)) * 20
+          ).astype(np.float32)
+  prev[rng.random(shape) < 0.01] = np.nan
+  cfg = mesh.IntegrationConfig(dt=0.001, gamma=0.0, k0=k0, k=0.1,
+                               stride=(40.0, 40.0), num_iters=150, max_iters=450,
+                               stop_v_max=0.0, fire=True, dt_max=1000.0,
+                               prefer_orig_order=poo)
+  x0 = np.zeros(shape, np.float32)
+  want, ek_w, t_w = mo.relax_mesh(x0, prev, cfg)
+  got, ek_g, t_g = mesh.relax_mesh(x0, prev, cfg)
+  assert t_g == t_w
+  np.testing.assert_allclose(got, want, rtol=0, atol=ATOL)
+  np.testing.assert_allclose(ek_g, ek_w, rtol=1e-4)
+
+
+def test_empty_mesh(mesh):
+  cfg = mesh.IntegrationConfig(dt=0.001, gamma=0.0, k0=0.1, k=0.1,
+                               stride=(40.0, 40.0), num_iters=5, max_iters=5,
+                               stop_v_max=0.0)
+  x = np.zeros((2, 0, 8, 8), np.float32)
+  out, e_kin, t = mesh.relax_mesh(x, None, cfg)
+  assert out.shape == x.shape and t == 5 and e_kin == [0.0]
+
+
+def test_device_tensor_roundtrip(mesh):
+  import torch
+  x = torch.zeros((2, 1, 40, 40), device='cuda')
+  prev = torch.randn((2, 1, 40, 40), device='cuda')
+  cfg = mesh.IntegrationConfig(dt=0.001, gamma=0.0, k0=0.1, k=0.1,
+                               stride=(40.0, 40.0), num_iters=50, max_iters=100,
+                               stop_v_max=0.0)
+  out, _, _ = mesh.relax_mesh(x, prev, cfg)
+  assert out.is_cuda and float(x.abs().max()) == 0.0  # input untouched
+  want, _, _ = mo.relax_mesh(x.cpu().numpy(), prev.cpu().numpy(), cfg)
+  np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=ATOL)
+
+
+def test_full_size_properties(mesh):
+  """BASELINE config 3 geometry (2048^2 nodes): size-independent properties."""
+  import torch
+  n = 2048
+  cfg = mesh.IntegrationConfig(dt=0.001, gamma=0.0, k0=0.1, k=0.1,
+                               stride=(40.0, 40.0), num_iters=200, max_iters=200,
+                               stop_v_max=0.0, fire=True, dt_max=1000.0,
+                               prefer_orig_order=True)
+  # (1) a uniform translation of prev is followed rigidly: no internal stress, so
+  #     every node sees the same force and the mesh stays flat to rounding.
+  prev = torch.full((2, 1, n, n), 3.0, device='cuda')
+  out, _, _ = mesh.relax_mesh(torch.zeros_like(prev), prev, cfg)
+  assert float((out - out[:, :, :1, :1]).abs().max()) < 1e-4
+  # (2) tiling invariance: the solution on the big mesh restricted to an interior
+  #     window equals the solution of the same problem solved as 4 stacked copies.
+  g = torch.Generator(device='cuda').manual_seed(0)
+  p1 = torch.randn((2, 1, 256, 256), device='cuda', generator=g) * 4
+  out1, ek1, _ = mesh.relax_mesh(torch.zeros_like(p1), p1, cfg)
+  p4 = p1.repeat(1, 4, 1, 1)
+  out4, ek4, _ = mesh.relax_mesh(torch.zeros_like(p4), p4, cfg)
+  # Independent sections share one global FIRE state (power is summed over z), so
+  # identical sections evolve identically.
+  for z in range(4):
+    assert torch.equal(out4[:, z], out1[:, 0])
+  np.testing.assert_allclose(ek4, np.array(ek1) * 4, rtol=1e-9)
+  # (3) determinism: two runs are bitwise identical.
+  out1b, _, _ = mesh.relax_mesh(torch.zeros_like(p1), p1, cfg)
+  assert torch.equal(out1, out1b)

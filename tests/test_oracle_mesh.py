@@ -1,0 +1,151 @@
+"""Pins oracle/mesh_oracle.py: reference KATs (tests/mesh_test.py) + golden vectors
+generated from the reference's own mesh.py (tests/golden/make_golden.py)."""
+
+import ast
+import types
+
+import numpy as np
+import pytest
+
+from oracle import mesh_oracle as mo
+from sofima_b200.mesh import IntegrationConfig
+
+
+def _cfg(golden, tag):
+  return IntegrationConfig(**ast.literal_eval(str(golden[f'{tag}_cfg'])))
+
+
+# ---- ports of /root/reference/tests/mesh_test.py ---------------------------------
+
+
+def _kat_x():
+  x = np.zeros((2, 1, 50, 50))
+  x[0, 0, 20:30, 10] = 3
+  x[0, 0, 20:30, 40] = -4
+  x[1, 0, 30, 10:20] = 2
+  return x
+
+
+def test_relaxation_fire():  # mesh_test.py:25-44
+  cfg = IntegrationConfig(dt=0.01, gamma=0.0, k0=0.1, k=0.1, stride=(10, 10),
+                          num_iters=100, max_iters=10000, stop_v_max=0.001,
+                          fire=True)
+  x = _kat_x()
+  new_x, _, _ = mo.relax_mesh(x, np.zeros_like(x), cfg)
+  np.testing.assert_array_almost_equal(new_x, np.zeros_like(x), decimal=3)
+
+
+def test_relaxation_damped():  # mesh_test.py:46-65
+  cfg = IntegrationConfig(dt=0.01, gamma=0.9 * np.sqrt(4 * 0.1), k0=0.1, k=0.1,
+                          stride=(10, 10), num_iters=100, max_iters=10000,
+                          stop_v_max=0.001, fire=False)
+  x = _kat_x()
+  new_x, _, _ = mo.relax_mesh(x, np.zeros_like(x), cfg)
+  np.testing.assert_array_almost_equal(new_x, np.zeros_like(x), decimal=3)
+
+
+def test_equilibrium():  # mesh_test.py:67-80
+  x = np.zeros((2, 1, 10, 10))
+  np.testing.assert_array_equal(x, mo.inplane_force(x, 1.0, (40.0, 40.0)))
+  x = np.zeros((3, 10, 10, 10))
+  np.testing.assert_array_equal(x, mo.elastic_mesh_3d(x, 1.0, 40.0))
+  x = np.zeros((3, 5, 10, 10, 10))
+  np.testing.assert_array_equal(x, mo.elastic_mesh_3d(x, 1.0, 40.0))
+
+
+def test_force_closed_form():  # mesh_test.py:82-120
+  x = np.zeros((2, 1, 10, 10))
+  dx, dy, k, l0 = 4, -3, 0.1, 10.0
+  x[0, 0, 5, 5], x[1, 0, 5, 5] = dx, dy
+  f = mo.inplane_force(x, k, (l0, 10))
+  l = np.sqrt((l0 + dx) ** 2 + dy**2)
+  np.testing.assert_allclose(
+      [k * (l - l0) * (l0 + dx) / l, k * (l - l0) * dy / l], f[:, 0, 5, 4],
+      rtol=1e-6)
+  l = np.sqrt(dx**2 + (l0 + dy) ** 2)
+  np.testing.assert_allclose(
+      [k * (l - l0) * dx / l, k * (l - l0) * (l0 + dy) / l], f[:, 0, 4, 5],
+      rtol=1e-6)
+  l2, k2 = l0 * np.sqrt(2.0), k / np.sqrt(2.0)
+  l = np.sqrt((l0 - dx) ** 2 + (l0 - dy) ** 2)
+  np.testing.assert_allclose(
+      [-k2 * (l - l2) * (l0 - dx) / l, -k2 * (l - l2) * (l0 - dy) / l],
+      f[:, 0, 6, 6], rtol=1e-5)
+  l = np.sqrt((l0 + dx) ** 2 + (l0 - dy) ** 2)
+  np.testing.assert_allclose(
+      [k2 * (l - l2) * (l0 + dx) / l, -k2 * (l - l2) * (l0 - dy) / l],
+      f[:, 0, 6, 4], rtol=1e-5)
+
+
+def test_2d_3d_consistency():  # mesh_test.py:122-144
+  planar = ((1, 0, 0), (0, 1, 0), (1, 1, 0), (-1, 1, 0))
+  x = np.random.default_rng(42).random((3, 1, 50, 50))
+  x[2] = 0.0
+  for poo in (False, True):
+    f2 = mo.inplane_force(x[:2], 0.01, (40.0, 40.0), poo)
+    f3 = mo.elastic_mesh_3d(x, 0.01, (40.0, 40.0, 14.0), poo, links=planar)
+    np.testing.assert_allclose(f2[:2], f3[:2], atol=1e-5)
+
+
+def test_relax_errors():  # mesh.py:556-568
+  base = dict(dt=0.01, gamma=0.0, k0=0.1, k=0.1, stride=(10, 10), num_iters=10,
+              max_iters=10, stop_v_max=0.1)
+  x = np.zeros((2, 1, 4, 4))
+  with pytest.raises(NotImplementedError):
+    mo.relax_mesh(x, x, IntegrationConfig(**base, fire=False, start_cap=1.0))
+  with pytest.raises(ValueError):
+    mo.relax_mesh(x, x, IntegrationConfig(**base, start_cap=1.0, cap_scale=1.0))
+  with pytest.raises(ValueError):
+    mo.relax_mesh(x, x, IntegrationConfig(**base), prev_fn=lambda a: a)
+  with pytest.raises(ValueError):
+    mo.inplane_force(x, 0.1, (1, 2, 3))
+
+
+# ---- golden vectors from the reference source ------------------------------------
+
+
+@pytest.mark.parametrize('poo', [0, 1])
+def test_golden_forces(mesh_golden, poo):
+  f = mo.inplane_force(mesh_golden['force2d_x'], 0.1, (40.0, 30.0), bool(poo))
+  np.testing.assert_array_equal(f, mesh_golden[f'force2d_poo{poo}'])
+  f = mo.elastic_mesh_3d(mesh_golden['force3d_x'], 0.1, (40.0, 40.0, 14.0),
+                         bool(poo))
+  np.testing.assert_array_equal(f, mesh_golden[f'force3d_poo{poo}'])
+
+
+@pytest.mark.parametrize(
+    'tag', ['fire_poo', 'fire_cap', 'fire_drift', 'damped', 'fire_nan_x', 'fire_3d'])
+def test_golden_chunks(mesh_golden, tag):
+  g = mesh_golden
+  cfg = _cfg(g, tag)
+  force = mo.elastic_mesh_3d if tag.endswith('3d') else mo.inplane_force
+  x = g[f'{tag}_x0']
+  v = np.zeros_like(x)
+  prev = g[f'{tag}_prev'] if f'{tag}_prev' in g.files else None
+  dt, alpha, cap = cfg.dt, cfg.alpha, cfg.start_cap
+  for i in range(g[f'{tag}_xs'].shape[0]):
+    st = mo.velocity_verlet(x, v, prev, cfg, cap, dt, alpha, mesh_force=force)
+    x, v = st[:2]
+    if cfg.fire:
+      dt, alpha, n_pos, cap = st[-4:]
+      np.testing.assert_allclose([dt, alpha, n_pos, cap], g[f'{tag}_scalars'][i],
+                                 rtol=1e-6)
+    # Bit-exact vs the reference source except where the fp32 summation order of
+    # np.mean (remove_drift) enters: there the north_star tolerance 1e-5 applies.
+    tol = 1e-5 if cfg.remove_drift else 0.0
+    np.testing.assert_allclose(x, g[f'{tag}_xs'][i], rtol=0, atol=tol)
+    np.testing.assert_allclose(v, g[f'{tag}_vs'][i], rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize('tag', ['kat_fire', 'kat_damped'])
+def test_golden_relax(mesh_golden, tag):
+  g = mesh_golden
+  fire = tag == 'kat_fire'
+  cfg = IntegrationConfig(dt=0.01, gamma=0.0 if fire else 0.9 * np.sqrt(4 * 0.1),
+                          k0=0.1, k=0.1, stride=(10, 10), num_iters=100,
+                          max_iters=10000, stop_v_max=0.001, fire=fire)
+  x0 = g[f'{tag}_x0']
+  x, ek, t = mo.relax_mesh(x0, np.zeros_like(x0), cfg)
+  assert t == int(g[f'{tag}_t'])
+  np.testing.assert_array_equal(x, g[f'{tag}_x'])
+  np.testing.assert_allclose(ek, g[f'{tag}_ekin'], rtol=1e-5)
