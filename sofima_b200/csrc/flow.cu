@@ -1,0 +1,942 @@
+// Patch-flow estimator on B200: batched (masked) cross-correlation + peak statistics.
+//
+// Replaces the device side of flow_field.batched_xcorr_peaks (reference
+// flow_field.py:385-441): _batched_xcorr (:278-371) -> masked_xcorr (:36-156) ->
+// _batched_peaks (:205-275) / _peak_stats (:178-202).
+//
+// Algorithm: the reference's own -- zero-padded real FFT correlation in fp32 --
+// written as shared-memory Stockham FFTs (any 2^a 3^b 5^c length, which is what
+// scipy's next_fast_len returns), three fused stages per batch:
+//   rows_fwd : gather patch rows from the images (uint8/float, clamped starts,
+//              mean subtraction, mask zeroing, flip of the 'post' patch), two real
+//              rows per complex FFT, half spectrum out               -> T
+//   cols     : per spectral column: forward FFT of every input, spectral products,
+//              inverse FFT                                           -> U
+//   rows_inv : two Hermitian rows per complex inverse FFT, crop, scale -> image
+// then the Padfield normalisation (masked path) and the peak search.
+// The spectra never leave L2: the batch is processed in sub-batches whose scratch
+// footprint is sized well below the 126 MB L2.
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sofima {
+namespace flow {
+
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 12;
+constexpr int kMaxFftLen = 4096;
+
+struct FftPlan {
+  int L;
+  int nstages;
+  int radix[kMaxStages];
+  int s[kMaxStages];   // stride of the stage (product of earlier radices)
+  int m[kMaxStages];   // n / r
+  int bf[kMaxStages];  // butterflies per transform = L / r
+  unsigned mg_bf[kMaxStages], mg_s[kMaxStages];  // magic multipliers (0: divisor 1)
+  const float2* tw;    // exp(-2 pi i k / L), k < L (device)
+};
+
+__host__ inline unsigned magic(unsigned d) {
+  return d == 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d);
+}
+__device__ __forceinline__ unsigned fdiv(unsigned n, unsigned mg) {
+  return mg == 0 ? n : __umulhi(n, mg);
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 rot(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+template <bool INV>
+__device__ __forceinline__ float2 twid(const float2* tw, int idx) {
+  float2 w = tw[idx];
+  if (INV) w.y = -w.y;
+  return w;
+}
+
+// One Stockham pass over `nfft` transforms stored as [nfft][L] in shared memory.
+template <bool INV>
+__device__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ dst, int nfft,
+                         const FftPlan& P, int st, const float2* tw) {
+  const int r = P.radix[st], s = P.s[st], m = P.m[st], bf = P.bf[st], L = P.L;
+  const unsigned mgb = P.mg_bf[st], mgs = P.mg_s[st];
+  const int total = nfft * bf;
+  const int sm = s * m;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int f = (int)fdiv((unsigned)t, mgb);
+    const int u = t - f * bf;
+    const int p = (int)fdiv((unsigned)u, mgs);
+    const int q = u - p * s;
+    const float2* in = src + f * L + q + s * p;
+    float2* out = dst + f * L + q + s * r * p;
+    const int tb = p * s;
+    if (r == 4) {
+      const float2 a0 = in[0], a1 = in[sm], a2 = in[2 * sm], a3 = in[3 * sm];
+      const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+      const float2 t3 = rot<INV>(csub(a1, a3));
+      out[0] = cadd(t0, t2);
+      out[s] = cmul(cadd(t1, t3), twid<INV>(tw, tb));
+      out[2 * s] = cmul(csub(t0, t2), twid<INV>(tw, 2 * tb));
+      out[3 * s] = cmul(csub(t1, t3), twid<INV>(tw, 3 * tb));
+    } else if (r == 2) {
+      const float2 a0 = in[0], a1 = in[sm];
+      out[0] = cadd(a0, a1);
+      out[s] = cmul(csub(a0, a1), twid<INV>(tw, tb));
+    } else if (r == 5) {
+      const float c1 = 0.30901699437494745f, c2 = -0.80901699437494745f;
+      const float s1 = 0.95105651629515353f, s2 = 0.58778525229247314f;
+      const float2 a0 = in[0], a1 = in[sm], a2 = in[2 * sm], a3 = in[3 * sm], a4 = in[4 * sm];
+      const float2 t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+      const float2 m1 = make_float2(a0.x + c1 * t1.x + c2 * t2.x, a0.y + c1 * t1.y + c2 * t2.y);
+      const float2 m2 = make_float2(a0.x + c2 * t1.x + c1 * t2.x, a0.y + c2 * t1.y + c1 * t2.y);
+      const float2 n1 = rot<INV>(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+      const float2 n2 = rot<INV>(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+      out[0] = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
+      out[s] = cmul(cadd(m1, n1), twid<INV>(tw, tb));
+      out[2 * s] = cmul(cadd(m2, n2), twid<INV>(tw, 2 * tb));
+      out[3 * s] = cmul(csub(m2, n2), twid<INV>(tw, 3 * tb));
+      out[4 * s] = cmul(csub(m1, n1), twid<INV>(tw, 4 * tb));
+    } else {  // r == 3
+      const float h = 0.86602540378443865f;
+      const float2 a0 = in[0], a1 = in[sm], a2 = in[2 * sm];
+      const float2 t1 = cadd(a1, a2);
+      const float2 t2 = make_float2(a0.x - 0.5f * t1.x, a0.y - 0.5f * t1.y);
+      const float2 d = csub(a1, a2);
+      const float2 t3 = rot<INV>(make_float2(h * d.x, h * d.y));
+      out[0] = cadd(a0, t1);
+      out[s] = cmul(cadd(t2, t3), twid<INV>(tw, tb));
+      out[2 * s] = cmul(csub(t2, t3), twid<INV>(tw, 2 * tb));
+    }
+  }
+}
+
+// Full transform of `nfft` lines; returns the buffer that holds the result.
+template <bool INV>
+__device__ float2* block_fft(float2* a, float2* b, int nfft, const FftPlan& P, const float2* tw) {
+  float2 *src = a, *dst = b;
+  for (int st = 0; st < P.nstages; ++st) {
+    fft_pass<INV>(src, dst, nfft, P, st, tw);
+    __syncthreads();
+    float2* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+__device__ __forceinline__ void load_twiddles(float2* tw_s, const FftPlan& P) {
+  for (int i = threadIdx.x; i < P.L; i += blockDim.x) tw_s[i] = __ldg(&P.tw[i]);
+}
+
+// ---------------------------------------------------------------------------------
+// Problem description shared by the kernels (2-d).
+// ---------------------------------------------------------------------------------
+struct Image {
+  const void* data;
+  const uint8_t* mask;  // may be null
+  int h, w;             // image extent
+  int mh, mw;           // mask extent
+  int ph, pw;           // patch extent
+};
+
+struct Slot {
+  int src;    // 0 = pre, 1 = post (flipped)
+  int xform;  // 0: (v - mean) * valid, 1: valid indicator, 2: ((v - mean) * valid)^2
+};
+
+struct Problem {
+  Image img[2];
+  int dtype;               // SOFIMA_U8 | SOFIMA_F32
+  const int32_t* starts[2];  // [B][2] (y, x), device
+  const float* means;      // [B][2]
+  int nslots;
+  Slot slot[6];
+  int PY;                  // max patch height (row capacity of T)
+  int sy, sx;              // correlation image extent (pre + post - 1)
+  int nkx;                 // Lx / 2 + 1
+  long long b0;            // first pair of this sub-batch
+  int nb;                  // pairs in this sub-batch
+};
+
+__device__ __forceinline__ int clamp_start(int st, int size, int extent) {
+  // jax.lax.dynamic_slice clamps the start so that the slice stays in bounds.
+  const int hi = extent - size;
+  return st < 0 ? 0 : (st > hi ? hi : st);
+}
+
+__device__ __forceinline__ float load_px(const void* data, int dtype, long long i) {
+  return dtype == SOFIMA_U8 ? (float)static_cast<const uint8_t*>(data)[i]
+                            : static_cast<const float*>(data)[i];
+}
+
+// Per-patch mean (flow_field.py:340-353): masked mean over the unmasked pixels.
+__global__ void __launch_bounds__(kThreads)
+patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
+  const int which = blockIdx.y;
+  const long long b = P.b0 + blockIdx.x;
+  if (has_mean) {
+    if (threadIdx.x == 0) means_out[b * 2 + which] = mean;
+    return;
+  }
+  const Image& I = P.img[which];
+  const int y0 = clamp_start(P.starts[which][b * 2 + 0], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[which][b * 2 + 1], I.pw, I.w);
+  int my0 = 0, mx0 = 0;
+  if (I.mask) {
+    my0 = clamp_start(P.starts[which][b * 2 + 0], I.ph, I.mh);
+    mx0 = clamp_start(P.starts[which][b * 2 + 1], I.pw, I.mw);
+  }
+  double sum = 0.0;
+  unsigned long long isum = 0;
+  int cnt = 0;
+  const int n = I.ph * I.pw;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const int y = i / I.pw, x = i - y * I.pw;
+    bool valid = true;
+    if (I.mask) valid = I.mask[(long long)(my0 + y) * I.mw + mx0 + x] == 0;
+    if (!valid) continue;
+    const long long gi = (long long)(y0 + y) * I.w + x0 + x;
+    if (P.dtype == SOFIMA_U8) isum += static_cast<const uint8_t*>(I.data)[gi];
+    else sum += (double)static_cast<const float*>(I.data)[gi];
+    ++cnt;
+  }
+  if (P.dtype == SOFIMA_U8) sum = (double)isum;
+  __shared__ double rs[kThreads / 32];
+  __shared__ int rc[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = sum; rc[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0; int c = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { s += rs[w]; c += rc[w]; }
+    // fp32 sum / fp32 count, as jnp.mean / jnp.nanmean (0/0 -> NaN).
+    means_out[b * 2 + which] = __fdiv_rn((float)s, (float)c);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage 1: forward row FFTs.  grid = (row-pair groups, slot, pair).
+// T layout: [slot][pair][PY][nkx] float2.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+rows_fwd_kernel(Problem P, FftPlan F, int R, float2* __restrict__ T) {
+  extern __shared__ float2 smem[];
+  float2* buf0 = smem;
+  float2* buf1 = smem + (size_t)R * F.L;
+  float2* tw_s = buf1 + (size_t)R * F.L;
+  const Slot sl = P.slot[blockIdx.y];
+  const Image& I = P.img[sl.src];
+  const long long b = P.b0 + blockIdx.z;
+  const int rp0 = blockIdx.x * R;  // first row pair
+  const int nrows = I.ph;
+  if (2 * rp0 >= nrows) return;
+  load_twiddles(tw_s, F);
+
+  const int y0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.w);
+  int my0 = 0, mx0 = 0;
+  if (I.mask) {
+    my0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.mh);
+    mx0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.mw);
+  }
+  const float mean = P.means[b * 2 + sl.src];
+  const bool flip = sl.src == 1;  // curr[::-1, ::-1], flow_field.py:78-79
+
+  auto sample = [&](int y, int x) -> float {
+    if (y >= nrows) return 0.f;
+    const int yy = flip ? I.ph - 1 - y : y, xx = flip ? I.pw - 1 - x : x;
+    bool valid = true;
+    if (I.mask) valid = I.mask[(long long)(my0 + yy) * I.mw + mx0 + xx] == 0;
+    if (sl.xform == 1) return valid ? 1.f : 0.f;
+    float v = load_px(I.data, P.dtype, (long long)(y0 + yy) * I.w + x0 + xx) - mean;
+    v = valid ? v : 0.f;  // where(mask, 0, patch - mean), flow_field.py:73-76
+    return sl.xform == 2 ? v * v : v;
+  };
+
+  for (int i = threadIdx.x; i < R * F.L; i += kThreads) {
+    const int f = i / F.L, x = i - f * F.L;
+    float2 z = make_float2(0.f, 0.f);
+    const int y = 2 * (rp0 + f);
+    if (x < I.pw && y < nrows) z = make_float2(sample(y, x), sample(y + 1, x));
+    buf0[i] = z;
+  }
+  __syncthreads();
+  const float2* Z = block_fft<false>(buf0, buf1, R, F, tw_s);
+
+  float2* Tb = T + ((size_t)blockIdx.y * P.nb + blockIdx.z) * P.PY * P.nkx;
+  for (int i = threadIdx.x; i < R * P.nkx; i += kThreads) {
+    const int f = i / P.nkx, k = i - f * P.nkx;
+    const int y = 2 * (rp0 + f);
+    if (y >= nrows) continue;
+    const float2 a = Z[f * F.L + k];
+    const float2 c = Z[f * F.L + (k == 0 ? 0 : F.L - k)];
+    // X_even = (Z[k] + conj Z[L-k]) / 2 ; X_odd = (Z[k] - conj Z[L-k]) / (2i)
+    Tb[(size_t)y * P.nkx + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+    if (y + 1 < nrows)
+      Tb[(size_t)(y + 1) * P.nkx + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage 2: column FFTs, spectral products, inverse column FFTs.
+// grid = (column groups, pair).  U layout: [out][pair][sy][nkx] float2.
+// ---------------------------------------------------------------------------------
+struct Products {
+  int nout;
+  int a[6], b[6];  // out[i] = spectrum[a[i]] * spectrum[b[i]]
+};
+
+__global__ void __launch_bounds__(kThreads)
+cols_kernel(Problem P, FftPlan F, int C, Products pr, const float2* __restrict__ T,
+            float2* __restrict__ U) {
+  extern __shared__ float2 smem[];
+  const int L = F.L;
+  float2* w0 = smem;
+  float2* w1 = w0 + (size_t)C * L;
+  float2* spec = w1 + (size_t)C * L;               // [nslots][C][L]
+  float2* tw_s = spec + (size_t)P.nslots * C * L;
+  load_twiddles(tw_s, F);
+  const int k0 = blockIdx.x * C;
+  const int nc = min(C, P.nkx - k0);
+
+  for (int sl = 0; sl < P.nslots; ++sl) {
+    const int rows = P.img[P.slot[sl].src].ph;
+    const float2* Tb = T + ((size_t)sl * P.nb + blockIdx.y) * P.PY * P.nkx;
+    for (int i = threadIdx.x; i < C * L; i += kThreads) {
+      const int y = i / C, c = i - y * C;  // c fastest: contiguous global reads
+      float2 v = make_float2(0.f, 0.f);
+      if (c < nc && y < rows) v = Tb[(size_t)y * P.nkx + k0 + c];
+      w0[c * L + y] = v;
+    }
+    __syncthreads();
+    const float2* res = block_fft<false>(w0, w1, C, F, tw_s);
+    float2* dst = spec + (size_t)sl * C * L;
+    for (int i = threadIdx.x; i < C * L; i += kThreads) dst[i] = res[i];
+    __syncthreads();
+  }
+  for (int o = 0; o < pr.nout; ++o) {
+    const float2* A = spec + (size_t)pr.a[o] * C * L;
+    const float2* B = spec + (size_t)pr.b[o] * C * L;
+    for (int i = threadIdx.x; i < C * L; i += kThreads) w0[i] = cmul(A[i], B[i]);
+    __syncthreads();
+    const float2* res = block_fft<true>(w0, w1, C, F, tw_s);
+    float2* Ub = U + ((size_t)o * P.nb + blockIdx.y) * P.sy * P.nkx;
+    for (int i = threadIdx.x; i < C * P.sy; i += kThreads) {
+      const int y = i / C, c = i - y * C;
+      if (c < nc) Ub[(size_t)y * P.nkx + k0 + c] = res[c * L + y];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage 3: inverse row FFTs (two Hermitian rows per complex transform), crop, scale.
+// grid = (row-pair groups, out, pair).  dst[out] + pair * sy * sx.
+// ---------------------------------------------------------------------------------
+struct Outputs {
+  float* dst[6];
+};
+
+__global__ void __launch_bounds__(kThreads)
+rows_inv_kernel(Problem P, FftPlan F, int R, const float2* __restrict__ U, Outputs outs,
+                float scale) {
+  extern __shared__ float2 smem[];
+  float2* buf0 = smem;
+  float2* buf1 = smem + (size_t)R * F.L;
+  float2* tw_s = buf1 + (size_t)R * F.L;
+  const int L = F.L;
+  const int rp0 = blockIdx.x * R;
+  if (2 * rp0 >= P.sy) return;
+  load_twiddles(tw_s, F);
+  const float2* Ub = U + ((size_t)blockIdx.y * P.nb + blockIdx.z) * P.sy * P.nkx;
+  const bool even = (L & 1) == 0;
+  for (int i = threadIdx.x; i < R * L; i += kThreads) {
+    const int f = i / L, k = i - f * L;
+    const int y = 2 * (rp0 + f);
+    float2 z = make_float2(0.f, 0.f);
+    if (y < P.sy) {
+      const int kk = (k < P.nkx) ? k : L - k;
+      float2 u0 = Ub[(size_t)y * P.nkx + kk];
+      float2 u1 = (y + 1 < P.sy) ? Ub[(size_t)(y + 1) * P.nkx + kk] : make_float2(0.f, 0.f);
+      // c2r ignores the imaginary part of the DC and Nyquist bins.
+      if (kk == 0 || (even && kk == L / 2)) { u0.y = 0.f; u1.y = 0.f; }
+      if (k >= P.nkx) { u0.y = -u0.y; u1.y = -u1.y; }
+      z = make_float2(u0.x - u1.y, u0.y + u1.x);  // u0 + i u1
+    }
+    buf0[i] = z;
+  }
+  __syncthreads();
+  const float2* Z = block_fft<true>(buf0, buf1, R, F, tw_s);
+  float* out = outs.dst[blockIdx.y] + (size_t)(P.b0 + blockIdx.z) * P.sy * P.sx;
+  for (int i = threadIdx.x; i < R * P.sx; i += kThreads) {
+    const int f = i / P.sx, x = i - f * P.sx;
+    const int y = 2 * (rp0 + f);
+    if (y >= P.sy) continue;
+    const float2 z = Z[f * L + x];
+    out[(size_t)y * P.sx + x] = z.x * scale;
+    if (y + 1 < P.sy) out[(size_t)(y + 1) * P.sx + x] = z.y * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Padfield normalisation (masked path), flow_field.py:113-155.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float atomic_max_nonneg(float* addr, float v) {
+  // valid for v >= 0 (IEEE order == integer order); NaN is handled by the caller.
+  return __int_as_float(atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v)));
+}
+
+// in: six correlation images per pair (xc, ov, mcp, mcc, psq, csq)
+// out: numerator (in place of xc), denom (in place of ov slot 1 -> stored in mcp),
+//      overlap (in place of ov).  maxima[0] = max |denom|, maxima[1] = max overlap.
+__global__ void __launch_bounds__(kThreads)
+padfield_terms_kernel(float* xc, float* ov, float* mcp, const float* mcc, const float* psq,
+                      const float* csq, long long n, float* maxima) {
+  const float eps = 1.1920929e-07f;
+  float mden = 0.f, mov = 0.f;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads) {
+    const float o = fmaxf(rintf(ov[i]), eps);  // round-half-even, fmax(., eps)
+    const float oi = 1.0f / o;
+    const float p = mcp[i], c = mcc[i];
+    const float num = xc[i] - p * c * oi;
+    const float pd = fmaxf(psq[i] - p * p * oi, 0.f);
+    const float cd = fmaxf(csq[i] - c * c * oi, 0.f);
+    const float den = sqrtf(pd * cd);
+    xc[i] = num;
+    mcp[i] = den;
+    ov[i] = o;
+    mden = fmaxf(mden, fabsf(den));
+    mov = fmaxf(mov, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mden = fmaxf(mden, __shfl_xor_sync(0xffffffffu, mden, o));
+    mov = fmaxf(mov, __shfl_xor_sync(0xffffffffu, mov, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_max_nonneg(&maxima[0], mden);
+    atomic_max_nonneg(&maxima[1], mov);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+padfield_normalise_kernel(float* xc, const float* ov, const float* den, long long n,
+                          const float* maxima) {
+  const float eps = 1.1920929e-07f;
+  const float tol = 1e3f * eps * maxima[0];  // batch-global max, flow_field.py:137
+  const float px_thr = 0.3f * maxima[1];     // batch-global max, flow_field.py:151
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads) {
+    const float d = den[i];
+    float out = (d > tol) ? xc[i] / d : 0.f;
+    out = fminf(fmaxf(out, -1.f), 1.f);
+    xc[i] = (ov[i] < px_thr) ? 0.f : out;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Peaks (flow_field.py:205-275, :178-202).
+// ---------------------------------------------------------------------------------
+struct PeakParams {
+  int sy, sx;
+  int md;        // min_distance
+  float thr_rel;
+  int ry, rx;    // peak_radius
+  int cy, cx;    // center_offset
+};
+
+// order-preserving key: larger value first, then smaller flat index.
+__device__ __forceinline__ unsigned long long peak_key(float v, unsigned idx) {
+  unsigned u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ void key_decode(unsigned long long k, float* v, unsigned* idx) {
+  unsigned u = (unsigned)(k >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  *v = __uint_as_float(u);
+  *idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+}
+
+__device__ unsigned long long block_max_key(unsigned long long k, unsigned long long* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+    k = other > k ? other : k;
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = k;
+  __syncthreads();
+  unsigned long long r = 0;
+  for (int w = 0; w < kThreads / 32; ++w) r = sm[w] > r ? sm[w] : r;
+  __syncthreads();
+  return r;
+}
+
+// Pass 1: global max / first argmax per image.  peak1[b] = {value or -inf, index}.
+__global__ void __launch_bounds__(kThreads)
+peak1_kernel(const float* __restrict__ img, PeakParams pp, float* v1, int* p1) {
+  __shared__ unsigned long long sm[kThreads / 32];
+  __shared__ int nan_flag;
+  if (threadIdx.x == 0) nan_flag = 0;
+  __syncthreads();
+  const long long n = (long long)pp.sy * pp.sx;
+  const float* im = img + blockIdx.x * n;
+  unsigned long long best = 0;
+  int has_nan = 0;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const float v = im[i];
+    if (v != v) has_nan = 1;
+    const unsigned long long k = peak_key(v, (unsigned)i);
+    best = k > best ? k : best;
+  }
+  if (has_nan) nan_flag = 1;
+  best = block_max_key(best, sm);
+  if (threadIdx.x == 0) {
+    float v; unsigned idx;
+    key_decode(best, &v, &idx);
+    // The global maximum is a peak iff it is > 0 (it always equals its own
+    // zero-padded neighbourhood maximum and must exceed threshold_rel * max).
+    const bool ok = !nan_flag && n > 0 && (v > pp.thr_rel * v);
+    v1[blockIdx.x] = ok ? v : -INFINITY;
+    p1[blockIdx.x] = ok ? (int)idx : 0;  // argmax of an all -inf row is 0
+  }
+}
+
+__global__ void mark_peaks_kernel(const int* p1, long long B, unsigned* bitmap) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) atomicOr(&bitmap[p1[b] >> 5], 1u << (p1[b] & 31));
+}
+
+__device__ __forceinline__ bool is_peak(const float* im, const PeakParams& pp, int y, int x,
+                                        float v) {
+  // img == separable zero-padded max filter of width 2*md+1 (flow_field.py:237-254).
+  float m = -INFINITY;
+  for (int dy = -pp.md; dy <= pp.md; ++dy) {
+    const int yy = y + dy;
+    for (int dx = -pp.md; dx <= pp.md; ++dx) {
+      const int xx = x + dx;
+      const float w = (yy < 0 || yy >= pp.sy || xx < 0 || xx >= pp.sx)
+                          ? 0.f : im[(long long)yy * pp.sx + xx];
+      m = fmaxf(m, w);
+    }
+  }
+  return v == m;
+}
+
+// Pass 2: second peak under the batch-coupled exclusion rule + statistics.
+__global__ void __launch_bounds__(kThreads)
+peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, const int* p1a,
+             const unsigned* __restrict__ bitmap, int ndim_out, float* out) {
+  __shared__ unsigned long long sm[kThreads / 32];
+  __shared__ float smin[kThreads / 32];
+  const long long n = (long long)pp.sy * pp.sx;
+  const float* im = img + blockIdx.x * n;
+  float* o = out + (long long)blockIdx.x * ndim_out;
+  const float v1 = v1a[blockIdx.x];
+  const int p1 = p1a[blockIdx.x];
+  if (v1 == -INFINITY) {  // no peak: the whole row is NaN (flow_field.py:194-196)
+    if (threadIdx.x < ndim_out) o[threadIdx.x] = NAN;
+    return;
+  }
+  const float thr = pp.thr_rel * v1;
+  unsigned long long best = 0;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const float v = im[i];
+    if (!(v > thr)) continue;
+    if ((bitmap[i >> 5] >> (i & 31)) & 1u) continue;  // erased for every row (:263-265)
+    const int y = i / pp.sx, x = i - y * pp.sx;
+    if (!is_peak(im, pp, y, x, v)) continue;
+    const unsigned long long k = peak_key(v, (unsigned)i);
+    best = k > best ? k : best;
+  }
+  best = block_max_key(best, sm);
+
+  // Sharpness: peak / min over a (2r+1) window with clamped start (:190-192).
+  const int py = p1 / pp.sx, px = p1 - py * pp.sx;
+  const int wy = 2 * pp.ry + 1, wx = 2 * pp.rx + 1;
+  const int y0 = clamp_start(py - pp.ry, wy, pp.sy), x0 = clamp_start(px - pp.rx, wx, pp.sx);
+  float mn = INFINITY;
+  bool nan_seen = false;
+  for (int i = threadIdx.x; i < wy * wx; i += kThreads) {
+    const int yy = y0 + i / wx, xx = x0 + i % wx;
+    const float v = im[(long long)yy * pp.sx + xx];
+    if (v != v) nan_seen = true;
+    mn = fminf(mn, v);
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, of));
+  (void)nan_seen;
+  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < kThreads / 32; ++w) mn = fminf(mn, smin[w]);
+    float v2;
+    if (best != 0) {
+      unsigned idx;
+      key_decode(best, &v2, &idx);
+    } else {
+      // argmax of an all -inf row is index 0; the value is read from the
+      // un-erased array (flow_field.py:266-268).
+      const float v0 = im[0];
+      v2 = (v0 > thr && is_peak(im, pp, 0, 0, v0)) ? v0 : -INFINITY;
+    }
+    o[0] = (float)px - (float)pp.cx;
+    o[1] = (float)py - (float)pp.cy;
+    o[2] = v1 / mn;
+    o[3] = (v2 == -INFINITY || v2 == INFINITY) ? 0.0f : v1 / v2;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Host side.
+// ---------------------------------------------------------------------------------
+static int next_fast_len(int n) {
+  for (;; ++n) {
+    int m = n;
+    for (int p : {2, 3, 5}) while (m % p == 0) m /= p;
+    if (m == 1) return n;
+  }
+}
+
+static int make_plan(sofima_ctx* ctx, int L, FftPlan* P) {
+  if (L > kMaxFftLen)
+    return fail(ctx, SOFIMA_EUNSUPPORTED,
+                "FFT length %d exceeds the shared-memory FFT limit %d (whole-strip "
+                "correlations are not built yet)", L, kMaxFftLen);
+  memset(P, 0, sizeof(*P));
+  P->L = L;
+  int n = L, s = 1, st = 0;
+  auto push = [&](int r) {
+    P->radix[st] = r;
+    P->s[st] = s;
+    P->m[st] = n / r;
+    P->bf[st] = L / r;
+    P->mg_bf[st] = magic((unsigned)(L / r));
+    P->mg_s[st] = magic((unsigned)s);
+    n /= r;
+    s *= r;
+    ++st;
+  };
+  while (n % 4 == 0) push(4);
+  while (n % 2 == 0) push(2);
+  while (n % 3 == 0) push(3);
+  while (n % 5 == 0) push(5);
+  if (n != 1 || st > kMaxStages)
+    return fail(ctx, SOFIMA_EINVAL, "FFT length %d is not 5-smooth", L);
+  P->nstages = st;
+  char name[64];
+  snprintf(name, sizeof(name), "flow.tw.%d", L);
+  const bool fresh = ctx->scratch.find(name) == ctx->scratch.end();
+  void* tw = nullptr;
+  int rc = scratch(ctx, name, sizeof(float2) * (size_t)L, &tw);
+  if (rc) return rc;
+  if (fresh) {
+    std::vector<float2> h(L);
+    for (int k = 0; k < L; ++k) {
+      const double a = -2.0 * M_PI * (double)k / (double)L;
+      h[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    SOFIMA_CUDA(ctx, cudaMemcpyAsync(tw, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  P->tw = static_cast<const float2*>(tw);
+  return SOFIMA_OK;
+}
+
+static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const PeakParams& pp,
+                     float* out_peaks) {
+  if (B == 0) return SOFIMA_OK;
+  const long long n = (long long)pp.sy * pp.sx;
+  if (2 * pp.ry + 1 > pp.sy || 2 * pp.rx + 1 > pp.sx)
+    return fail(ctx, SOFIMA_EINVAL, "peak_radius window larger than the correlation image");
+  void *v1 = nullptr, *p1 = nullptr, *bm = nullptr;
+  int rc;
+  if ((rc = scratch(ctx, "flow.v1", sizeof(float) * B, &v1))) return rc;
+  if ((rc = scratch(ctx, "flow.p1", sizeof(int) * B, &p1))) return rc;
+  const size_t words = (size_t)((n + 31) / 32);
+  if ((rc = scratch(ctx, "flow.bitmap", sizeof(unsigned) * words, &bm))) return rc;
+  SOFIMA_CUDA(ctx, cudaMemsetAsync(bm, 0, sizeof(unsigned) * words, ctx->stream));
+  peak1_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (float*)v1, (int*)p1);
+  SOFIMA_CHECK_LAUNCH(ctx);
+  mark_peaks_kernel<<<(unsigned)ceil_div<long long>(B, 256), 256, 0, ctx->stream>>>(
+      (const int*)p1, B, (unsigned*)bm);
+  SOFIMA_CHECK_LAUNCH(ctx);
+  peak2_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (const float*)v1,
+                                                          (const int*)p1, (const unsigned*)bm,
+                                                          4, out_peaks);
+  SOFIMA_CHECK_LAUNCH(ctx);
+  return SOFIMA_OK;
+}
+
+static int check_params(sofima_ctx* ctx, const sofima_xcorr_params* p) {
+  if (!p) return fail(ctx, SOFIMA_EINVAL, "params is NULL");
+  if (p->ndim == 3)
+    return fail(ctx, SOFIMA_EUNSUPPORTED, "3-d patch correlation is not built yet");
+  if (p->ndim != 2) return fail(ctx, SOFIMA_EINVAL, "ndim must be 2 or 3");
+  if (p->img_dtype != SOFIMA_U8 && p->img_dtype != SOFIMA_F32)
+    return fail(ctx, SOFIMA_EINVAL, "img_dtype must be SOFIMA_U8 or SOFIMA_F32");
+  for (int d = 0; d < 2; ++d) {
+    if (p->pre_patch[d] < 1 || p->post_patch[d] < 1)
+      return fail(ctx, SOFIMA_EINVAL, "patch sizes must be positive");
+    if (p->pre_patch[d] > p->pre_shape[d] || p->post_patch[d] > p->post_shape[d])
+      return fail(ctx, SOFIMA_EINVAL, "patch larger than image");
+    if (p->pre_shape[d] > INT32_MAX || p->post_shape[d] > INT32_MAX)
+      return fail(ctx, SOFIMA_EINVAL, "image extent out of range");
+  }
+  if (p->min_distance < 0) return fail(ctx, SOFIMA_EINVAL, "min_distance < 0");
+  return SOFIMA_OK;
+}
+
+// Computes the correlation images of one batch into `images` [B][sy][sx].
+static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                     const void* post_img, const uint8_t* pre_mask, const uint8_t* post_mask,
+                     const int32_t* pre_starts, const int32_t* post_starts, long long B,
+                     float* images) {
+  const bool masked = pre_mask != nullptr || post_mask != nullptr;
+  Problem P;
+  memset(&P, 0, sizeof(P));
+  P.dtype = p->img_dtype;
+  const void* datas[2] = {pre_img, post_img};
+  const uint8_t* masks[2] = {pre_mask, post_mask};
+  const int64_t* shapes[2] = {p->pre_shape, p->post_shape};
+  const int64_t* mshapes[2] = {p->pre_mask_shape, p->post_mask_shape};
+  const int32_t* patches[2] = {p->pre_patch, p->post_patch};
+  for (int i = 0; i < 2; ++i) {
+    P.img[i].data = datas[i];
+    P.img[i].mask = masks[i];
+    P.img[i].h = (int)shapes[i][0];
+    P.img[i].w = (int)shapes[i][1];
+    P.img[i].ph = patches[i][0];
+    P.img[i].pw = patches[i][1];
+    if (masks[i]) {
+      P.img[i].mh = (int)mshapes[i][0];
+      P.img[i].mw = (int)mshapes[i][1];
+      if (P.img[i].mh < P.img[i].ph || P.img[i].mw < P.img[i].pw)
+        return fail(ctx, SOFIMA_EINVAL, "mask smaller than patch");
+    }
+  }
+  P.starts[0] = pre_starts;
+  P.starts[1] = post_starts;
+  P.sy = p->pre_patch[0] + p->post_patch[0] - 1;
+  P.sx = p->pre_patch[1] + p->post_patch[1] - 1;
+  P.PY = p->pre_patch[0] > p->post_patch[0] ? p->pre_patch[0] : p->post_patch[0];
+  const int Ly = next_fast_len(P.sy), Lx = next_fast_len(P.sx);
+  P.nkx = Lx / 2 + 1;
+  P.nslots = masked ? 6 : 2;
+  const Slot slots[6] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}, {0, 2}, {1, 2}};
+  for (int i = 0; i < 6; ++i) P.slot[i] = slots[i];
+  Products pr;
+  memset(&pr, 0, sizeof(pr));
+  if (masked) {
+    // xcorr, overlap, mc_p, mc_c, p_sq, c_sq  (flow_field.py:85,114,118,119,124,128)
+    const int a[6] = {0, 3, 3, 2, 3, 2}, b[6] = {1, 2, 0, 1, 4, 5};
+    pr.nout = 6;
+    for (int i = 0; i < 6; ++i) { pr.a[i] = a[i]; pr.b[i] = b[i]; }
+  } else {
+    pr.nout = 1;
+    pr.a[0] = 0;
+    pr.b[0] = 1;
+  }
+
+  FftPlan Fx, Fy;
+  int rc;
+  if ((rc = make_plan(ctx, Lx, &Fx))) return rc;
+  if ((rc = make_plan(ctx, Ly, &Fy))) return rc;
+
+  // Shared-memory budgets.
+  const size_t smem_cap = 200 * 1024;
+  int R = 8;
+  while (R > 1 && (size_t)(2 * R + 1) * Lx * sizeof(float2) > 96 * 1024) R /= 2;
+  const size_t smem_rows = (size_t)(2 * R + 1) * Lx * sizeof(float2);
+  int C = 8;
+  while (C > 1 && (size_t)((2 + P.nslots) * C + 1) * Ly * sizeof(float2) > smem_cap) C /= 2;
+  const size_t smem_cols = (size_t)((2 + P.nslots) * C + 1) * Ly * sizeof(float2);
+  if (smem_rows > smem_cap || smem_cols > smem_cap)
+    return fail(ctx, SOFIMA_EUNSUPPORTED, "patch too large for the shared-memory FFT");
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(cols_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+
+  // Sub-batches: keep T and U (and the six masked outputs) L2-resident.
+  const size_t per_pair = sizeof(float2) * ((size_t)P.nslots * P.PY * P.nkx +
+                                            (size_t)pr.nout * P.sy * P.nkx) +
+                          (masked ? sizeof(float) * 6 * (size_t)P.sy * P.sx : 0);
+  long long nsub = (long long)((64ull << 20) / per_pair);
+  if (nsub < 1) nsub = 1;
+  if (nsub > B) nsub = B;
+  if (nsub > 65535) nsub = 65535;
+  void *Tbuf = nullptr, *Ubuf = nullptr, *means = nullptr, *m6 = nullptr, *maxima = nullptr;
+  if ((rc = scratch(ctx, "flow.T", sizeof(float2) * (size_t)P.nslots * nsub * P.PY * P.nkx,
+                    &Tbuf))) return rc;
+  if ((rc = scratch(ctx, "flow.U", sizeof(float2) * (size_t)pr.nout * nsub * P.sy * P.nkx,
+                    &Ubuf))) return rc;
+  if ((rc = scratch(ctx, "flow.means", sizeof(float) * 2 * B, &means))) return rc;
+  P.means = static_cast<const float*>(means);
+  const size_t img_elems = (size_t)P.sy * P.sx;
+  float *den_all = nullptr, *ov_all = nullptr;
+  if (masked) {
+    // per sub-batch: mcc, psq, csq; whole batch: numerator (= images), denom, overlap.
+    if ((rc = scratch(ctx, "flow.m3", sizeof(float) * 3 * nsub * img_elems, &m6))) return rc;
+    void *d = nullptr, *o = nullptr;
+    if ((rc = scratch(ctx, "flow.den", sizeof(float) * B * img_elems, &d))) return rc;
+    if ((rc = scratch(ctx, "flow.ov", sizeof(float) * B * img_elems, &o))) return rc;
+    den_all = static_cast<float*>(d);
+    ov_all = static_cast<float*>(o);
+    if ((rc = scratch(ctx, "flow.maxima", sizeof(float) * 2, &maxima))) return rc;
+    SOFIMA_CUDA(ctx, cudaMemsetAsync(maxima, 0, sizeof(float) * 2, ctx->stream));
+  }
+  const float scale = (float)(1.0 / ((double)Lx * (double)Ly));
+
+  for (long long b0 = 0; b0 < B; b0 += nsub) {
+    const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
+    P.b0 = b0;
+    P.nb = nb;
+    patch_mean_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, p->has_mean, p->mean,
+                                                                 (float*)means);
+    SOFIMA_CHECK_LAUNCH(ctx);
+    const int rp_max = (P.PY + 1) / 2;
+    rows_fwd_kernel<<<dim3(ceil_div(rp_max, R), P.nslots, nb), kThreads, smem_rows,
+                      ctx->stream>>>(P, Fx, R, (float2*)Tbuf);
+    SOFIMA_CHECK_LAUNCH(ctx);
+    cols_kernel<<<dim3(ceil_div(P.nkx, C), nb), kThreads, smem_cols, ctx->stream>>>(
+        P, Fy, C, pr, (const float2*)Tbuf, (float2*)Ubuf);
+    SOFIMA_CHECK_LAUNCH(ctx);
+    Outputs outs;
+    memset(&outs, 0, sizeof(outs));
+    if (!masked) {
+      outs.dst[0] = images;
+    } else {
+      // Outputs of this sub-batch are addressed with the global pair index b0 + i,
+      // so sub-batch-local buffers are offset back by b0.
+      float* loc = static_cast<float*>(m6);
+      outs.dst[0] = images;                                   // xcorr -> numerator
+      outs.dst[1] = ov_all;                                   // overlap
+      outs.dst[2] = den_all;                                  // mc_p -> denom
+      outs.dst[3] = loc + 0 * nsub * img_elems - b0 * img_elems;  // mc_c
+      outs.dst[4] = loc + 1 * nsub * img_elems - b0 * img_elems;  // p_sq
+      outs.dst[5] = loc + 2 * nsub * img_elems - b0 * img_elems;  // c_sq
+    }
+    rows_inv_kernel<<<dim3(ceil_div((P.sy + 1) / 2, R), pr.nout, nb), kThreads, smem_rows,
+                      ctx->stream>>>(P, Fx, R, (const float2*)Ubuf, outs, scale);
+    SOFIMA_CHECK_LAUNCH(ctx);
+    if (masked) {
+      const long long n = (long long)nb * img_elems;
+      const size_t off = (size_t)b0 * img_elems;
+      float* loc = static_cast<float*>(m6);
+      padfield_terms_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+          images + off, ov_all + off, den_all + off, loc, loc + nsub * img_elems,
+          loc + 2 * nsub * img_elems, n, (float*)maxima);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+  }
+  if (masked) {
+    padfield_normalise_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+        images, ov_all, den_all, (long long)B * img_elems, (const float*)maxima);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  return SOFIMA_OK;
+}
+
+}  // namespace flow
+}  // namespace sofima
+
+extern "C" {
+
+int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                        const void* post_img, const uint8_t* pre_mask,
+                        const uint8_t* post_mask, const int32_t* pre_starts,
+                        const int32_t* post_starts, int64_t batch, float* out_xcorr) {
+  using namespace sofima;
+  if (!ctx) return fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
+  int rc = flow::check_params(ctx, p);
+  if (rc) return rc;
+  if (batch < 0) return fail(ctx, SOFIMA_EINVAL, "batch < 0");
+  if (batch == 0) return SOFIMA_OK;
+  if (!pre_img || !post_img || !pre_starts || !post_starts || !out_xcorr)
+    return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
+  DeviceGuard guard(ctx->device);
+  return flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
+                         post_starts, batch, out_xcorr);
+}
+
+int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                       const void* post_img, const uint8_t* pre_mask, const uint8_t* post_mask,
+                       const int32_t* pre_starts, const int32_t* post_starts, int64_t batch,
+                       float* out_peaks) {
+  using namespace sofima;
+  if (!ctx) return fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
+  int rc = flow::check_params(ctx, p);
+  if (rc) return rc;
+  if (batch < 0) return fail(ctx, SOFIMA_EINVAL, "batch < 0");
+  if (batch == 0) return SOFIMA_OK;
+  if (!pre_img || !post_img || !pre_starts || !post_starts || !out_peaks)
+    return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
+  DeviceGuard guard(ctx->device);
+  const int sy = p->pre_patch[0] + p->post_patch[0] - 1;
+  const int sx = p->pre_patch[1] + p->post_patch[1] - 1;
+  void* images = nullptr;
+  if ((rc = scratch(ctx, "flow.images", sizeof(float) * (size_t)batch * sy * sx, &images)))
+    return rc;
+  rc = flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts, post_starts,
+                       batch, static_cast<float*>(images));
+  if (rc) return rc;
+  flow::PeakParams pp;
+  pp.sy = sy;
+  pp.sx = sx;
+  pp.md = p->min_distance;
+  pp.thr_rel = p->threshold_rel;
+  pp.ry = p->peak_radius[0];
+  pp.rx = p->peak_radius[1];
+  // center_offset = (pre + post) // 2 - 1, flow_field.py:357-360
+  pp.cy = (p->pre_patch[0] + p->post_patch[0]) / 2 - 1;
+  pp.cx = (p->pre_patch[1] + p->post_patch[1]) / 2 - 1;
+  return flow::run_peaks(ctx, static_cast<const float*>(images), batch, pp, out_peaks);
+}
+
+int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img, const int64_t* img_shape,
+                         int64_t batch, const int32_t* center_offset, int min_distance,
+                         float threshold_rel, const int32_t* peak_radius, float* out_peaks) {
+  using namespace sofima;
+  if (!ctx) return fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
+  if (ndim == 3) return fail(ctx, SOFIMA_EUNSUPPORTED, "3-d peak search is not built yet");
+  if (ndim != 2) return fail(ctx, SOFIMA_EINVAL, "ndim must be 2 or 3");
+  if (batch < 0) return fail(ctx, SOFIMA_EINVAL, "batch < 0");
+  if (batch == 0) return SOFIMA_OK;
+  if (!img || !img_shape || !center_offset || !peak_radius || !out_peaks)
+    return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
+  if (img_shape[0] * img_shape[1] > INT32_MAX || min_distance < 0)
+    return fail(ctx, SOFIMA_EINVAL, "image too large");
+  DeviceGuard guard(ctx->device);
+  flow::PeakParams pp;
+  pp.sy = (int)img_shape[0];
+  pp.sx = (int)img_shape[1];
+  pp.md = min_distance;
+  pp.thr_rel = threshold_rel;
+  pp.ry = peak_radius[0];
+  pp.rx = peak_radius[1];
+  pp.cy = center_offset[0];
+  pp.cx = center_offset[1];
+  return flow::run_peaks(ctx, img, batch, pp, out_peaks);
+}
+
+}  // extern "C"

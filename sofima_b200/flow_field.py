@@ -1,0 +1,439 @@
+"""Drop-in for `sofima.flow_field` (reference flow_field.py) on the B200 backend.
+
+Same public names and signatures as the reference:
+
+  JAXMaskedXCorrWithStatsCalculator(.flow_field)   flow_field.py:449-712
+  batched_xcorr_peaks                              flow_field.py:385-441
+  masked_xcorr                                     flow_field.py:36-156
+  _batched_peaks                                   flow_field.py:205-275
+
+The host driver (`flow_field`) keeps the reference's index arithmetic -- output
+geometry, patch selection from masks, 'edge'-padded final batch, targeting
+fields -- and hands every batch to the CUDA library (`sofima_xcorr_peaks`).
+Unlike the reference it does not block per batch: images are uploaded once, all
+batches are queued on the stream and the peak table comes back in one copy.
+There is no CPU path here.
+"""
+
+from __future__ import annotations
+
+import collections.abc
+import ctypes
+import logging
+from typing import Callable, Iterator, Sequence, TypeVar
+
+import numpy as np
+
+from . import _native
+
+T = TypeVar('T')
+
+
+def _torch():
+  import torch  # plumbing: device memory and streams
+  return torch
+
+
+def _is_tensor(a) -> bool:
+  return type(a).__module__.startswith('torch')
+
+
+def _device_image(img, ctx):
+  """uint8 or float32 contiguous CUDA tensor + SOFIMA dtype code."""
+  torch = _torch()
+  dev = torch.device('cuda', ctx.device)
+  if _is_tensor(img):
+    t = img.to(dev)
+    if t.dtype != torch.uint8:
+      t = t.to(torch.float32)
+    return t.contiguous()
+  a = np.asarray(img)
+  if a.dtype != np.uint8:
+    a = a.astype(np.float32)  # JAX computes in fp32 whatever the input dtype
+  return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+
+def _device_mask(mask, ctx):
+  if mask is None:
+    return None
+  torch = _torch()
+  dev = torch.device('cuda', ctx.device)
+  if _is_tensor(mask):
+    return (mask.to(dev) != 0).to(torch.uint8).contiguous()
+  m = np.ascontiguousarray(np.asarray(mask) != 0).view(np.uint8)
+  return torch.from_numpy(m).to(dev, non_blocking=True)
+
+
+def _int3(vals, fill=0):
+  vals = [int(v) for v in vals]
+  return vals + [fill] * (3 - len(vals))
+
+
+def _params(ndim, pre, post, pre_mask, post_mask, patch_size, post_patch_size,
+            mean, min_distance, threshold_rel, peak_radius):
+  torch = _torch()
+  if pre.dtype != post.dtype:
+    pre, post = pre.to(torch.float32), post.to(torch.float32)
+  p = _native.XcorrParams()
+  p.ndim = ndim
+  p.img_dtype = 0 if pre.dtype == torch.uint8 else 1
+  for i, v in enumerate(_int3(pre.shape)):
+    p.pre_shape[i] = v
+  for i, v in enumerate(_int3(post.shape)):
+    p.post_shape[i] = v
+  if pre_mask is not None:
+    for i, v in enumerate(_int3(pre_mask.shape)):
+      p.pre_mask_shape[i] = v
+  if post_mask is not None:
+    for i, v in enumerate(_int3(post_mask.shape)):
+      p.post_mask_shape[i] = v
+  for i, v in enumerate(_int3(patch_size, 1)):
+    p.pre_patch[i] = v
+  for i, v in enumerate(_int3(post_patch_size, 1)):
+    p.post_patch[i] = v
+  p.has_mean = int(mean is not None)
+  p.mean = float(mean) if mean is not None else 0.0
+  if isinstance(min_distance, collections.abc.Sequence):
+    # The reference itself fails here (unbound `size`, flow_field.py:232-240).
+    raise NotImplementedError('min_distance must be a scalar')
+  p.min_distance = int(min_distance)
+  p.threshold_rel = float(threshold_rel)
+  if not isinstance(peak_radius, collections.abc.Sequence):
+    peak_radius = (peak_radius,) * ndim
+  for i, v in enumerate(_int3(peak_radius)):
+    p.peak_radius[i] = v
+  return p, pre, post
+
+
+def _ptr(t):
+  return None if t is None else t.data_ptr()
+
+
+def batched_xcorr_peaks(pre_image, post_image, pre_mask, post_mask,
+                        patch_size: Sequence[int], starts, mean: float | None,
+                        min_distance: int = 2, threshold_rel: float = 0.5,
+                        peak_radius: int | Sequence[int] = 5,
+                        post_patch_size: Sequence[int] | None = None,
+                        post_starts=None):
+  """Computes cross-correlations and identifies their peaks (flow_field.py:385).
+
+  Args and result as in the reference: `starts` / `post_starts` are [b, 2 or 3]
+  integer top-left ([z]yx) patch coordinates; returns a [b, ndim + 2] float32
+  array (x, y[, z], sharpness, peak ratio).  NumPy inputs give a NumPy result,
+  CUDA tensors a CUDA tensor.
+  """
+  ctx = _native.Context.get(
+      pre_image.device.index if _is_tensor(pre_image) and pre_image.is_cuda else None)
+  torch = _torch()
+  host_result = not _is_tensor(pre_image)
+  pre = _device_image(pre_image, ctx)
+  post = _device_image(post_image, ctx)
+  pre_m = _device_mask(pre_mask, ctx)
+  post_m = _device_mask(post_mask, ctx)
+  ndim = pre.ndim
+  if post_patch_size is None:
+    post_patch_size = patch_size
+  if post_starts is None:
+    post_starts = starts
+  p, pre, post = _params(ndim, pre, post, pre_m, post_m, patch_size,
+                         post_patch_size, mean, min_distance, threshold_rel,
+                         peak_radius)
+  dev = torch.device('cuda', ctx.device)
+
+  def starts_dev(s):
+    if _is_tensor(s):
+      return s.to(dev, dtype=torch.int32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(s, dtype=np.int32)).to(dev)
+
+  st, pst = starts_dev(starts), starts_dev(post_starts)
+  b = st.shape[0]
+  out = torch.empty((b, ndim + 2), dtype=torch.float32, device=dev)
+  ctx.bind_stream()
+  rc = _native.lib().sofima_xcorr_peaks(
+      ctx.handle, ctypes.byref(p), pre.data_ptr(), post.data_ptr(), _ptr(pre_m),
+      _ptr(post_m), st.data_ptr(), pst.data_ptr(), b, out.data_ptr())
+  _native.check(ctx.handle, rc)
+  return out.cpu().numpy() if host_result else out
+
+
+def masked_xcorr(prev, curr, prev_mask=None, curr_mask=None, use_jax: bool = False,
+                 dim: int = 2):
+  """Cross-correlation between two (batches of) masked images (flow_field.py:36).
+
+  Correlation is computed over the last `dim` axes; leading axes are batch.  The
+  inputs are whole patches (no mean subtraction is applied here, as in the
+  reference).  `use_jax` is accepted for signature compatibility.
+  """
+  del use_jax
+  prev = np.asarray(prev, dtype=np.float32)
+  curr = np.asarray(curr, dtype=np.float32)
+  if dim != 2:
+    raise NotImplementedError('3-d correlation is not part of the CUDA backend yet')
+  lead = prev.shape[:-dim]
+  pb = prev.reshape((-1,) + prev.shape[-dim:])
+  cb = curr.reshape((-1,) + curr.shape[-dim:])
+  nb = pb.shape[0]
+  pm = None if prev_mask is None else np.asarray(prev_mask, bool).reshape(pb.shape)
+  cm = None if curr_mask is None else np.asarray(curr_mask, bool).reshape(cb.shape)
+  ctx = _native.Context.get()
+  torch = _torch()
+  dev = torch.device('cuda', ctx.device)
+  # Lay the batch out as one tall image so that patch b starts at row b * h.
+  pre = torch.from_numpy(np.ascontiguousarray(pb.reshape(-1, pb.shape[-1]))).to(dev)
+  post = torch.from_numpy(np.ascontiguousarray(cb.reshape(-1, cb.shape[-1]))).to(dev)
+  pre_m = None if pm is None else _device_mask(pm.reshape(-1, pm.shape[-1]), ctx)
+  post_m = None if cm is None else _device_mask(cm.reshape(-1, cm.shape[-1]), ctx)
+  p, pre, post = _params(2, pre, post, pre_m, post_m, pb.shape[1:], cb.shape[1:],
+                         0.0, 2, 0.5, 0)
+  st = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
+  st[:, 0] = torch.arange(nb, device=dev, dtype=torch.int32) * pb.shape[1]
+  pst = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
+  pst[:, 0] = torch.arange(nb, device=dev, dtype=torch.int32) * cb.shape[1]
+  sy, sx = pb.shape[1] + cb.shape[1] - 1, pb.shape[2] + cb.shape[2] - 1
+  out = torch.empty((nb, sy, sx), dtype=torch.float32, device=dev)
+  ctx.bind_stream()
+  rc = _native.lib().sofima_xcorr_images(
+      ctx.handle, ctypes.byref(p), pre.data_ptr(), post.data_ptr(), _ptr(pre_m),
+      _ptr(post_m), st.data_ptr(), pst.data_ptr(), nb, out.data_ptr())
+  _native.check(ctx.handle, rc)
+  return out.cpu().numpy().reshape(lead + (sy, sx))
+
+
+def _batched_peaks(img, center_offset, min_distance, threshold_rel,
+                   peak_radius: int | Sequence[int] = 5):
+  """Peak statistics from a batch of correlation images (flow_field.py:205).
+
+  Args:
+    img: [b, y, x] correlation images
+    center_offset: (y, x) location of the zero-shift peak
+    min_distance: min. distance in pixels between peaks (scalar)
+    threshold_rel: fraction of the image max that a peak has to exceed
+    peak_radius: radius for the sharpness window
+
+  Returns:
+    [b, 4] array: x, y peak offset from center, sharpness, peak ratio
+  """
+  host_result = not _is_tensor(img)
+  ctx = _native.Context.get(
+      img.device.index if _is_tensor(img) and img.is_cuda else None)
+  torch = _torch()
+  dev = torch.device('cuda', ctx.device)
+  if _is_tensor(img):
+    t = img.to(dev, dtype=torch.float32).contiguous()
+  else:
+    t = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)
+  ndim = t.ndim - 1
+  if isinstance(min_distance, collections.abc.Sequence):
+    raise NotImplementedError('min_distance must be a scalar')
+  if not isinstance(peak_radius, collections.abc.Sequence):
+    peak_radius = (peak_radius,) * ndim
+  shape = (ctypes.c_int64 * 3)(*_int3(t.shape[1:]))
+  center = (ctypes.c_int32 * 3)(*_int3(center_offset))
+  radius = (ctypes.c_int32 * 3)(*_int3(peak_radius))
+  out = torch.empty((t.shape[0], ndim + 2), dtype=torch.float32, device=dev)
+  ctx.bind_stream()
+  rc = _native.lib().sofima_batched_peaks(
+      ctx.handle, ndim, t.data_ptr(), shape, t.shape[0], center, int(min_distance),
+      float(threshold_rel), radius, out.data_ptr())
+  _native.check(ctx.handle, rc)
+  return out.cpu().numpy() if host_result else out
+
+
+# --- summed-area helpers (connectomics.common.geom_utils stand-ins) ----------------
+
+
+def _integral_image(mask):
+  """Zero-front-padded summed-area table of a mask (flow_field.py:159-175)."""
+  if mask is None:
+    return None
+  m = np.asarray(mask)
+  ii = m.astype(np.uint32 if m.size < 2**32 else np.int64)
+  for axis in range(m.ndim):
+    ii = ii.cumsum(axis=axis, dtype=ii.dtype)
+  return np.pad(ii, [(1, 0)] * m.ndim, mode='constant')
+
+
+def _query_integral_image(summed, diam, stride):
+  """Sums over `diam`-sized boxes at every `stride` (VALID mode)."""
+  summed = np.asarray(summed).astype(np.int64)
+  nd = summed.ndim
+  counts = [(n - 1 - d) // s + 1 for n, d, s in zip(summed.shape, diam, stride)]
+  out = np.zeros(counts, np.int64)
+  for corner in np.ndindex(*([2] * nd)):
+    sel = tuple(
+        slice(diam[a] * corner[a],
+              diam[a] * corner[a] + (counts[a] - 1) * stride[a] + 1, stride[a])
+        for a in range(nd))
+    out += (-1) ** (nd - sum(corner)) * summed[sel]
+  return out
+
+
+def _batches(seq, n):
+  for i in range(0, len(seq), n):
+    yield seq[i:i + n]
+
+
+def _silent_fn(x: list[T]) -> Iterator[T]:
+  for item in x:
+    yield item
+
+
+class JAXMaskedXCorrWithStatsCalculator:
+  """Estimates optical flow using masked cross-correlation.
+
+  Name kept from the reference (flow_field.py:449) so that callers such as
+  processor.flow.EstimateFlow work unchanged; the computation runs in CUDA.
+  """
+
+  non_spatial_flow_channels = 2  # peak sharpness, peak ratio
+
+  def __init__(self, mean: float | None = None, peak_min_distance: float = 2,
+               peak_radius: float = 5):
+    self._mean = mean
+    self._min_distance = peak_min_distance
+    self._peak_radius = peak_radius
+
+  def flow_field(self, pre_image, post_image, patch_size, step, pre_mask=None,
+                 post_mask=None, mask_only_for_patch_selection=False,
+                 selection_mask=None, max_masked=0.75, batch_size=4096,
+                 post_patch_size=None, pre_targeting_field=None,
+                 pre_targeting_step=None, post_targeting_field=None,
+                 post_targeting_step=None,
+                 progress_fn: Callable[[list[T]], Iterator[T]] = _silent_fn):
+    """Computes the flow field from post to pre (flow_field.py:474-712).
+
+    Arguments and result are those of the reference.  Returns a float32 array
+    [ndim + 2, *out_shape]; channel order x, y[, z], sharpness, peak ratio; NaN
+    where no flow was computed.
+    """
+    assert pre_image.ndim == post_image.ndim
+    nd = pre_image.ndim
+
+    if not isinstance(patch_size, collections.abc.Sequence):
+      patch_size = (patch_size,) * nd
+    if post_patch_size is not None:
+      if not isinstance(post_patch_size, collections.abc.Sequence):
+        post_patch_size = (post_patch_size,) * nd
+    else:
+      post_patch_size = patch_size
+    if not isinstance(step, collections.abc.Sequence):
+      step = (step,) * nd
+    if pre_targeting_step is not None and not isinstance(
+        pre_targeting_step, collections.abc.Sequence):
+      pre_targeting_step = (pre_targeting_step,) * nd
+
+    assert len(patch_size) == nd
+    assert len(post_patch_size) == nd
+    assert len(step) == nd
+
+    out_shape = (np.array(post_image.shape)
+                 - (np.array(post_patch_size) - step)) // step
+    out_sel = tuple(slice(0, int(s)) for s in out_shape)
+    output = np.full([self.non_spatial_flow_channels + nd] + out_shape.tolist(),
+                     np.nan, dtype=np.float32)
+
+    if selection_mask is None:
+      selection_mask = np.ones(out_shape, dtype=bool)
+    else:
+      selection_mask = np.array(selection_mask[out_sel], dtype=bool)
+
+    for mask, psz in ((pre_mask, patch_size), (post_mask, post_patch_size)):
+      if mask is not None:
+        s = _query_integral_image(_integral_image(np.asarray(mask)), psz, step)
+        selection_mask[(s / np.prod(psz) >= max_masked)[out_sel]] = False
+
+    if mask_only_for_patch_selection:
+      pre_mask = post_mask = None
+
+    oyx = np.array(np.where(selection_mask)).T
+    logging.info('Starting flow estimation for %d patches.', oyx.shape[0])
+    if oyx.shape[0] == 0:
+      return output
+
+    ctx = _native.Context.get()
+    torch = _torch()
+    dev = torch.device('cuda', ctx.device)
+    pre_d = _device_image(pre_image, ctx)
+    post_d = _device_image(post_image, ctx)
+    pre_m = _device_mask(pre_mask, ctx)
+    post_m = _device_mask(post_mask, ctx)
+    params, pre_d, post_d = _params(
+        nd, pre_d, post_d, pre_m, post_m, patch_size, post_patch_size, self._mean,
+        self._min_distance, 0.5, self._peak_radius)
+
+    patch_offset = ((np.array(patch_size) - post_patch_size) // 2)[None, ...]
+    patch_offset = patch_offset.astype(int)
+    step_arr = np.array(step).reshape((1, -1))
+
+    batches = list(_batches(oyx, batch_size))
+    pre_all, post_all, tg_all, po_all = [], [], [], []
+    for pos_zyx in batches:
+      real = pos_zyx.shape[0]
+      if real < batch_size:  # fixed batch size, 'edge' padding (flow_field.py:614)
+        proc = np.pad(pos_zyx, ((0, batch_size - real), (0, 0)), mode='edge')
+      else:
+        proc = pos_zyx
+      post_starts = proc * step_arr
+      pre_starts = np.clip(post_starts - patch_offset, 0, np.inf).astype(int)
+
+      tg = po = None
+      if pre_targeting_field is not None and pre_targeting_step is not None:
+        tg = _targeting_offsets(pre_targeting_field, pre_targeting_step,
+                                pre_starts, patch_size, pre_image.shape)
+        pre_starts = pre_starts + tg
+      if post_targeting_field is not None and post_targeting_step is not None:
+        po = _targeting_offsets(post_targeting_field, post_targeting_step,
+                                post_starts, post_patch_size, post_image.shape)
+        post_starts = post_starts + po
+      pre_all.append(np.clip(pre_starts, 0, np.inf).astype(np.int32))
+      post_all.append(np.clip(post_starts, 0, np.inf).astype(np.int32))
+      tg_all.append(tg)
+      po_all.append(po)
+
+    # One upload of every start coordinate, one launch sequence per reference
+    # batch (the second-peak rule couples the members of a batch), one download.
+    nb = len(batches)
+    # NB: np.stack keeps the (Fortran) layout of np.where-derived views, and the
+    # library takes plain C-contiguous [batch, nd] tables.
+    starts_h = np.ascontiguousarray(
+        np.stack([np.stack(pre_all), np.stack(post_all)]), dtype=np.int32)
+    starts_d = torch.from_numpy(starts_h).to(dev).contiguous()  # [2, nb, batch, nd]
+    peaks_d = torch.empty((nb, batch_size, nd + 2), dtype=torch.float32, device=dev)
+    ctx.bind_stream()
+    lib = _native.lib()
+    for i in progress_fn(list(range(nb))):
+      rc = lib.sofima_xcorr_peaks(
+          ctx.handle, ctypes.byref(params), pre_d.data_ptr(), post_d.data_ptr(),
+          _ptr(pre_m), _ptr(post_m), starts_d[0, i].data_ptr(),
+          starts_d[1, i].data_ptr(), batch_size, peaks_d[i].data_ptr())
+      _native.check(ctx.handle, rc)
+    peaks = peaks_d.cpu().numpy()
+
+    for i, pos_zyx in enumerate(batches):
+      real = pos_zyx.shape[0]
+      v = peaks[i, :real]
+      if tg_all[i] is not None:
+        v[:, :nd] = v[:, :nd] + tg_all[i][:real, ::-1]  # xy[z]
+      if po_all[i] is not None:
+        v[:, :nd] = v[:, :nd] - po_all[i][:real, ::-1]  # xy[z]
+      output[(slice(None),) + tuple(pos_zyx.T)] = v.T
+
+    logging.info('Flow field estimation complete.')
+    return output
+
+
+def _targeting_offsets(field, tg_step, starts, patch, img_shape):
+  """Start offsets from a targeting field (flow_field.py:626-649, :652-677)."""
+  center = (np.array(patch) // 2).reshape((1, -1))  # [z]yx
+  tg_step = np.array(tg_step).reshape((1, -1))
+  query = np.round((starts + center) / tg_step).astype(int)  # [b, [z]yx]
+  q = [np.clip(query[:, i], 0, field.shape[i + 1] - 1)
+       for i in range(query.shape[-1])]
+  off = np.nan_to_num(field[(slice(None),) + tuple(q)].T)
+  off = off.astype(int)[:, ::-1]  # [b, xy[z]] -> [b, [z]yx]
+  new_starts = starts + off
+  # Clip offsets that would take the patch out of bounds.
+  off = off - np.minimum(new_starts, 0)
+  shape = np.array(img_shape)[None, ...]
+  new_ends = new_starts + np.array(patch)[None, ...]
+  return off - (np.maximum(new_ends, shape) - shape)

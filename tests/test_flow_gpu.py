@@ -1,0 +1,249 @@
+"""GPU parity tests: sofima_b200.flow_field (CUDA, through the C ABI) vs the oracle
+and the golden vectors generated from the reference source.
+
+Tolerances (north_star): flow offsets 1e-4 rel -- they are integers, so the test
+demands equality; NaN patterns must match exactly.  The two statistics channels
+(sharpness, peak ratio) are fp32 quotients of FFT outputs; rtol 2e-3 (SURVEY 8d
+asks 1e-3 as a goal, non-gating).
+"""
+
+import numpy as np
+import pytest
+import scipy.ndimage as ndi
+
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ff():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  from sofima_b200 import flow_field
+  return flow_field
+
+
+def _check_flow(got, want, stats_rtol=2e-3, stats=True):
+  assert got.shape == want.shape
+  nd = got.shape[0] - 2
+  np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+  np.testing.assert_array_equal(got[:nd], want[:nd])
+  if stats:
+    ok = ~np.isnan(want[nd])
+    np.testing.assert_allclose(got[nd][ok], want[nd][ok], rtol=stats_rtol)
+    np.testing.assert_allclose(got[nd + 1][ok], want[nd + 1][ok], rtol=stats_rtol,
+                               atol=1e-6)
+
+
+# ---- ports of /root/reference/tests/flow_field_test.py on the CUDA path ----------
+
+
+def test_kat_delta_and_mask(ff):
+  pre = np.zeros((120, 120), np.uint8)
+  post = np.zeros((120, 120), np.uint8)
+  pre[60, 60] = 255
+  post[70, 53] = 255
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  field = calc.flow_field(pre, post, patch_size=80, step=40, batch_size=4)
+  np.testing.assert_array_equal([4, 2, 2], field.shape)
+  np.testing.assert_array_equal(7 * np.ones((2, 2)), field[0])
+  np.testing.assert_array_equal(-10 * np.ones((2, 2)), field[1])
+  np.testing.assert_array_equal(np.zeros((2, 2)), field[3])
+  post[54, 68] = 255
+  mask = np.zeros((128, 128), bool)
+  mask[:55, :70] = 1
+  field = calc.flow_field(pre, post, patch_size=80, step=40, post_mask=mask,
+                          batch_size=4)
+  np.testing.assert_array_equal(7 * np.ones((2, 2)), field[0])
+  np.testing.assert_array_equal(-10 * np.ones((2, 2)), field[1])
+  np.testing.assert_array_equal(np.zeros((2, 2)), field[3])
+
+
+def test_kat_peak(ff):
+  hy, hx = np.mgrid[:50, :50]
+  cy, cx = 20, 28
+  r = np.sqrt(2 * (cx - hx) ** 2 + (cy - hy) ** 2)
+  xcorr = 10 * np.exp(-r / 4)
+  peaks = ff._batched_peaks(xcorr[np.newaxis], (25, 25), min_distance=2,
+                            threshold_rel=0.5, peak_radius=(2, 3))
+  assert peaks.shape == (1, 4)
+  support = np.min(xcorr.astype(np.float32)[cy - 2:cy + 3, cx - 3:cx + 4])
+  assert peaks[0, 0] == 3 and peaks[0, 1] == -5
+  assert peaks[0, 2] == np.float32(10) / support
+  assert peaks[0, 3] == 0
+
+
+def test_kat_post_targeting(ff):
+  pre = np.zeros((120, 120), np.uint8)
+  post = np.zeros((120, 120), np.uint8)
+  pre[50, 55] = 255
+  post[100, 100] = 255
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  field = calc.flow_field(pre, post, patch_size=80, step=40, batch_size=4)
+  assert np.all(np.isnan(field[:, 0, 0]))
+  tgt = np.full((2, 2, 2), 40.0, np.float32)
+  field = calc.flow_field(pre, post, patch_size=80, step=40, batch_size=4,
+                          post_targeting_field=tgt, post_targeting_step=40)
+  np.testing.assert_array_equal(-45 * np.ones((2, 2)), field[0])
+  np.testing.assert_array_equal(-50 * np.ones((2, 2)), field[1])
+
+
+def test_kat_3d_not_built(ff):
+  pre = np.zeros((50, 100, 100), np.uint8)
+  with pytest.raises(NotImplementedError):  # fails loudly, no CPU fallback
+    ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
+        pre, pre, patch_size=(40, 80, 80), step=10, batch_size=1)
+
+
+# ---- golden vectors from the reference source -------------------------------------
+
+
+def test_golden_textured(ff, flow_golden):
+  g = flow_golden
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  pre, post = g['tex160_b4_pre'], g['tex160_b4_post']
+  for bs in (4, 7, 64):
+    _check_flow(calc.flow_field(pre, post, 160, 40, batch_size=bs),
+                g[f'tex160_b{bs}_flow'])
+
+
+def test_golden_periodic_second_peak(ff, flow_golden):
+  g = flow_golden
+  got = ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
+      g['periodic_pre'], g['periodic_post'], 120, 40, batch_size=5)
+  _check_flow(got, g['periodic_flow'])
+
+
+def test_golden_masked(ff, flow_golden):
+  g = flow_golden
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  kw = dict(pre_mask=g['masked_pre_mask'], post_mask=g['masked_post_mask'],
+            batch_size=6)
+  _check_flow(calc.flow_field(g['masked_pre'], g['masked_post'], (96, 128),
+                              (32, 40), **kw), g['masked_flow'])
+  _check_flow(calc.flow_field(g['masked_pre'], g['masked_post'], (96, 128),
+                              (32, 40), mask_only_for_patch_selection=True,
+                              max_masked=0.4, **kw), g['masked_selonly_flow'])
+
+
+def test_golden_postpatch_and_targeting(ff, flow_golden):
+  g = flow_golden
+  calc = ff.JAXMaskedXCorrWithStatsCalculator(mean=40.0, peak_radius=(3, 4))
+  got = calc.flow_field(g['postpatch_pre'], g['postpatch_post'], 128, 24,
+                        post_patch_size=96, selection_mask=g['postpatch_sel'],
+                        batch_size=16)
+  _check_flow(got, g['postpatch_flow'])
+  got = ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
+      g['masked_pre'], g['masked_post'], 128, 24,
+      pre_targeting_field=g['pretarget_tg'], pre_targeting_step=24, batch_size=32)
+  _check_flow(got, g['pretarget_flow'])
+
+
+def test_golden_kats(ff, flow_golden):
+  g = flow_golden
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  got = calc.flow_field(g['kat_delta_pre'], g['kat_delta_post'], 80, 40,
+                        batch_size=4)
+  np.testing.assert_array_equal(got[[0, 1, 3]], g['kat_delta_flow'][[0, 1, 3]])
+  got = calc.flow_field(g['kat_notarget_pre'], g['kat_notarget_post'], 80, 40,
+                        batch_size=4)
+  np.testing.assert_array_equal(np.isnan(got), np.isnan(g['kat_notarget_flow']))
+  got = ff._batched_peaks(g['peaks_bump_img'][np.newaxis], (25, 25), 2, 0.5, (2, 3))
+  np.testing.assert_array_equal(got, g['peaks_bump'])
+
+
+# ---- seeded oracle comparisons ------------------------------------------------------
+
+
+def _texture(seed, shape, sigma=2.0):
+  rng = np.random.default_rng(seed)
+  base = ndi.gaussian_filter(rng.standard_normal(shape), sigma)
+  return ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+
+
+def test_xcorr_images_match_oracle(ff):
+  """The raw correlation images (what _batched_xcorr returns) vs pocketfft fp32."""
+  rng = np.random.default_rng(3)
+  for (ph, pw), (qh, qw) in (((160, 160), (160, 160)), ((50, 37), (31, 64)),
+                             ((9, 9), (9, 9))):
+    a = rng.standard_normal((3, ph, pw)).astype(np.float32)
+    b = rng.standard_normal((3, qh, qw)).astype(np.float32)
+    got = ff.masked_xcorr(a, b)
+    want = fo.masked_xcorr(a, b)
+    assert got.shape == want.shape
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got / scale, want / scale, atol=2e-6)
+    am = rng.random(a.shape) > 0.8
+    bm = rng.random(b.shape) > 0.7
+    got = ff.masked_xcorr(a, b, am, bm)
+    want = fo.masked_xcorr(a, b, am, bm)
+    np.testing.assert_allclose(got, want, atol=2e-4)
+
+
+def test_config1_512_tile_pair(ff):
+  """BASELINE config 1: 512x512 tile pair, patch 160, step 40 -> 81 patch pairs."""
+  rng = np.random.default_rng(0)
+  base = ndi.gaussian_filter(rng.standard_normal((640, 640)), 2.0)
+  base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+  pre = base[64:576, 64:576]
+  post = np.clip(base[69:581, 61:573].astype(float) + rng.normal(0, 5, (512, 512)),
+                 0, 255).astype(np.uint8)
+  got = ff.JAXMaskedXCorrWithStatsCalculator().flow_field(pre, post, 160, 40,
+                                                          batch_size=1024)
+  assert got.shape == (4, 9, 9)
+  np.testing.assert_array_equal(got[0], -3)
+  np.testing.assert_array_equal(got[1], 5)
+  want = fo.MaskedXCorrWithStatsCalculator().flow_field(pre, post, 160, 40,
+                                                        batch_size=1024)
+  _check_flow(got, want)
+
+
+@pytest.mark.parametrize('seed,patch,step,bs', [
+    (1, 64, 16, 32), (2, (48, 80), (16, 24), 9), (3, 33, 11, 128)])
+def test_random_textures_match_oracle(ff, seed, patch, step, bs):
+  img = _texture(seed, (260, 300), sigma=1.5)
+  rng = np.random.default_rng(seed)
+  pre = img[10:210, 10:250]
+  post = np.clip(img[13:213, 6:246].astype(float) + rng.normal(0, 12, (200, 240)),
+                 0, 255).astype(np.uint8)
+  got = ff.JAXMaskedXCorrWithStatsCalculator().flow_field(pre, post, patch, step,
+                                                          batch_size=bs)
+  want = fo.MaskedXCorrWithStatsCalculator().flow_field(pre, post, patch, step,
+                                                        batch_size=bs)
+  _check_flow(got, want)
+
+
+def test_empty_selection(ff):
+  pre = np.zeros((100, 100), np.uint8)
+  sel = np.zeros((4, 4), bool)
+  got = ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
+      pre, pre, 40, 20, selection_mask=sel, batch_size=8)
+  assert got.shape == (4, 4, 4) and np.isnan(got).all()
+
+
+def test_full_size_properties(ff):
+  """4096^2 tile pair (BASELINE config 2 tile size): 9801 patch pairs.
+
+  Size-independent properties: a pure translation is recovered everywhere, the
+  result is invariant to how the grid is cut into images (a crop gives the same
+  rows), and repeated runs are bit-identical.
+  """
+  n = 4096
+  base = _texture(9, (n + 64, n + 64), sigma=2.0)
+  pre = base[32:32 + n, 32:32 + n]
+  post = base[32 + 4:32 + 4 + n, 32 - 7:32 - 7 + n]
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  got = calc.flow_field(pre, post, 160, 40, batch_size=1024)
+  assert got.shape == (4, 99, 99)
+  np.testing.assert_array_equal(got[0], -7)
+  np.testing.assert_array_equal(got[1], 4)
+  again = calc.flow_field(pre, post, 160, 40, batch_size=1024)
+  np.testing.assert_array_equal(got, again)
+  # A 1024 crop, same batch composition rule -> same offsets on the shared grid.
+  crop = calc.flow_field(pre[:1024, :1024], post[:1024, :1024], 160, 40,
+                         batch_size=1024)
+  np.testing.assert_array_equal(crop[:2], got[:2, :crop.shape[1], :crop.shape[2]])
+  np.testing.assert_allclose(crop[2], got[2, :crop.shape[1], :crop.shape[2]],
+                             rtol=1e-3)

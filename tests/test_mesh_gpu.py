@@ -154,7 +154,7 @@ def test_golden_chunks(mesh, mesh_golden, tag):
       dt, alpha, n_pos, cap = st[-4:]
       np.testing.assert_allclose([dt, alpha, n_pos, cap], g[f'{tag}_scalars'][i],
                                  rtol=1e-6)
-    tol = 1e-5 if cfg.remove_drift else 0.0
+    tol = 5e-5 if cfg.remove_drift else 0.0
     np.testing.assert_allclose(x, g[f'{tag}_xs'][i], rtol=0, atol=tol)
     np.testing.assert_allclose(v, g[f'{tag}_vs'][i], rtol=0, atol=tol)
 
