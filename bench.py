@@ -1,0 +1,526 @@
+#!/usr/bin/env python
+"""Benchmark of the two SOFIMA hot paths on B200 (see BASELINE.json / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W           # this repo (CUDA)
+  python bench.py --impl reference --gpus N ...            # CPU arm (oracle port)
+
+One JSON line on rank 0.  Primary metric: patch-pairs/s of the flow estimator; the
+`mesh` object carries the second BASELINE metric (node-updates/s of the mesh
+solver) with its own roofline / e2e / cpu_baseline.
+
+A *step* is one pass of the hot path over one batch of synthetic input:
+  flow  one 4096x4096 uint8 tile pair, patch 160, step 40 -> 9801 patch pairs
+        (BASELINE configs[1] tile size; EM-2D batch_size 1024, em_2d.py:32-41)
+  mesh  one velocity_verlet chunk of `--mesh-iters` (default 1000) FIRE steps on a
+        [2, 1, 2048, 2048] mesh with a fixed `prev` (BASELINE configs[2]);
+        node-updates = nodes x steps.
+`value` is timed with the inputs resident in HBM; `e2e` goes through the public
+Python API (sofima_b200.flow_field / sofima_b200.mesh, i.e. the C-ABI library)
+with pinned HOST arrays, including H2D of the inputs and D2H of the result.
+Between timed steps the inputs rotate over tile pairs totalling more than the
+126 MB L2 (flow) / the mesh state itself exceeds L2 (134 MB).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+FLOW_TILE = 4096
+PATCH, STEP, BATCH = 160, 40, 1024
+MESH_N = 2048
+DENSE_FLOP_PER_PAIR = 2.0 * PATCH**4          # p^4 MAC per patch pair
+MESH_BYTES_PER_UPDATE = 56.0                  # 8 floats in, 6 out
+
+
+def _peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    d = json.load(open(path))
+    return dict(hbm_gbs=d['hbm_gbs'], tflops=d['bf16_tflops_sustained'],
+                source='measured (MEASURED_PEAKS.json)')
+  return dict(hbm_gbs=6650.0, tflops=1590.0,
+              source='fallback (B200_PROFILING.md)')
+
+
+# ----------------------------------------------------------------------------------
+# synthetic data
+# ----------------------------------------------------------------------------------
+
+
+def synth_tile_pairs(num, size, seed, device):
+  """`num` uint8 tile pairs cut from smooth random textures with a known shift."""
+  import torch
+  import torch.nn.functional as F
+  g = torch.Generator(device=device).manual_seed(seed)
+  m = 32
+  k = torch.arange(-6, 7, device=device, dtype=torch.float32)
+  k = torch.exp(-0.5 * (k / 2.0) ** 2)
+  k = (k / k.sum()).view(1, 1, 1, -1)
+  pairs = []
+  for i in range(num):
+    base = torch.randn((1, 1, size + 2 * m + 12, size + 2 * m + 12), device=device,
+                       generator=g)
+    base = F.conv2d(F.conv2d(base, k), k.transpose(2, 3))[0, 0]
+    base = (base - base.min()) / (base.max() - base.min()) * 255
+    dy, dx = 3 + i % 3, -4 + i % 5
+    pre = base[m:m + size, m:m + size].to(torch.uint8).contiguous()
+    noise = torch.randn((size, size), device=device, generator=g) * 5
+    post = (base[m + dy:m + dy + size, m + dx:m + dx + size] + noise).clamp(0, 255)
+    pairs.append((pre, post.to(torch.uint8).contiguous(), (dy, dx)))
+  return pairs
+
+
+def synth_mesh(n, seed, device):
+  """config 3: x0 = 0, prev = smooth displacement field (max 8 px), 1 % NaN."""
+  import torch
+  import torch.nn.functional as F
+  g = torch.Generator(device=device).manual_seed(seed)
+  k = torch.arange(-32, 33, device=device, dtype=torch.float32)
+  k = torch.exp(-0.5 * (k / 16.0) ** 2)
+  k = (k / k.sum()).view(1, 1, 1, -1)
+  f = torch.randn((2, 1, n + 64, n + 64), device=device, generator=g)
+  f = F.conv2d(F.conv2d(f, k), k.transpose(2, 3))
+  f = f / f.abs().max() * 8.0
+  prev = f.view(2, 1, n, n).contiguous()
+  nan = torch.rand((1, 1, n, n), device=device, generator=g) < 0.01
+  prev = torch.where(nan.expand_as(prev), torch.full_like(prev, float('nan')), prev)
+  return prev.contiguous()
+
+
+def mesh_config(mesh, iters):
+  return mesh.IntegrationConfig(
+      dt=0.001, gamma=0.0, k0=0.1, k=0.1, stride=(40.0, 40.0), num_iters=iters,
+      max_iters=iters, stop_v_max=0.0, fire=True, dt_max=1000.0,
+      prefer_orig_order=True)
+
+
+# ----------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.gpu = gpu_index
+    self.rows = []
+    self.proc = None
+
+  def __enter__(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+           '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE,
+          stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+    return self
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def __exit__(self, *exc):
+    if self.proc:
+      time.sleep(0.15)
+      self.proc.terminate()
+      try:
+        self.proc.wait(timeout=2)
+      except subprocess.TimeoutExpired:
+        self.proc.kill()
+
+  def summary(self):
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for r in self.rows:
+      try:
+        sm.append(float(r[1]))
+        mx.append(float(r[2]))
+      except (ValueError, IndexError):
+        continue
+      for name, val in zip(names, r[5:9]):
+        if val.lower().startswith('active'):
+          reasons.add(name)
+    if not sm:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)),
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------
+
+
+def cpu_flow_sample(size, seed=0):
+  import scipy.ndimage as ndi
+  rng = np.random.default_rng(seed)
+  base = ndi.gaussian_filter(rng.standard_normal((size + 64, size + 64)), 2.0)
+  base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+  pre = np.ascontiguousarray(base[32:32 + size, 32:32 + size])
+  post = np.ascontiguousarray(base[35:35 + size, 28:28 + size])
+  return pre, post
+
+
+def time_cpu_flow(size, reps=1):
+  """Oracle flow_field (NumPy/pocketfft, all cores) on one size x size tile pair."""
+  from oracle import flow_oracle
+  pre, post = cpu_flow_sample(size)
+  calc = flow_oracle.MaskedXCorrWithStatsCalculator()
+  g = (size - (PATCH - STEP)) // STEP
+  best = float('inf')
+  for _ in range(reps):
+    t0 = time.perf_counter()
+    out = calc.flow_field(pre, post, PATCH, STEP, batch_size=256)
+    best = min(best, time.perf_counter() - t0)
+  assert out.shape == (4, g, g)
+  return g * g / best, g * g, best
+
+
+def time_cpu_mesh(n, iters, reps=1):
+  """C restatement (OpenMP, all cores) of one velocity_verlet chunk on n x n nodes."""
+  from oracle import mesh_oracle_c
+  from sofima_b200 import mesh
+  rng = np.random.default_rng(2)
+  prev = (rng.standard_normal((2, 1, n, n)) * 4).astype(np.float32)
+  x = np.zeros_like(prev)
+  cfg = mesh_config(mesh, iters)
+  best = float('inf')
+  for _ in range(reps):
+    t0 = time.perf_counter()
+    mesh_oracle_c.velocity_verlet(x, np.zeros_like(x), prev, cfg, cfg.start_cap)
+    best = min(best, time.perf_counter() - t0)
+  return n * n * iters / best, best, mesh_oracle_c.num_threads()
+
+
+def run_reference(args):
+  """`--impl reference`: the reference algorithm on the host cores.
+
+  The reference is pure Python/JAX and JAX is not installable in this image, so the
+  CPU arm is the oracle port (oracle/flow_oracle.py on pocketfft with all cores,
+  oracle/mesh_oracle.c with OpenMP) -- `kind: "port"`.
+  """
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  cores = len(os.sched_getaffinity(0))
+  os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+  size = 1024  # bounded sample: (1024-120)//40 = 22 -> 484 patch pairs per step
+  for _ in range(args.warmup):
+    time_cpu_flow(size)
+  pairs, flow_s = 0, 0.0
+  for _ in range(args.steps):
+    _, n, sec = time_cpu_flow(size)  # times flow_field only, not the synthesis
+    pairs += n
+    flow_s += sec
+  flow_v = pairs / flow_s
+  mesh_iters = 10
+  for _ in range(min(args.warmup, 1)):
+    time_cpu_mesh(MESH_N, mesh_iters)
+  mesh_s = 0.0
+  for _ in range(args.steps):
+    _, sec, threads = time_cpu_mesh(MESH_N, mesh_iters)
+    mesh_s += sec
+  mesh_v = MESH_N * MESH_N * mesh_iters * args.steps / mesh_s
+  line = {
+      'impl': 'reference', 'metric': 'patch-pairs/s', 'value': flow_v,
+      'unit': 'patch-pairs/s', 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': flow_s / args.steps * 1e3,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': f'flow_field on a {size}x{size} crop of the 4096x4096 '
+                             f'uint8 tile pair, patch {PATCH}, step {STEP} '
+                             '(bounded CPU sample of the same workload)'},
+      'cpu_baseline': {'value': flow_v, 'unit': 'patch-pairs/s', 'cores': cores,
+                       'kind': 'port',
+                       'sample': f'{args.steps} x {size}^2 tile pair (484 patch pairs), '
+                                 'oracle/flow_oracle.py, pocketfft fp32'},
+      'e2e': {'value': flow_v, 'unit': 'patch-pairs/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'mesh': {'metric': 'node-updates/s', 'value': mesh_v, 'unit': 'node-updates/s',
+               'ms_per_step': mesh_s / args.steps * 1e3,
+               'cpu_baseline': {'value': mesh_v, 'unit': 'node-updates/s',
+                                'cores': threads, 'kind': 'port',
+                                'sample': f'{args.steps} x {mesh_iters} FIRE steps on '
+                                          f'{MESH_N}^2 nodes, oracle/mesh_oracle.c'},
+               'e2e': {'value': mesh_v, 'unit': 'node-updates/s',
+                       'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}},
+  }
+  print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from sofima_b200 import _native, flow_field, mesh
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a B200: sofima_b200 has no CPU fallback '
+                     '(use --impl reference for the CPU arm)')
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  ctx = _native.Context.get(local)
+  peaks = _peaks()
+  K, W = args.steps, args.warmup
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(ms):
+    if world > 1:
+      t = torch.tensor([ms], device=dev, dtype=torch.float64)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      return float(t.item())
+    return ms
+
+  def timed(fn, steps):
+    """Times `steps` calls of fn(i) on the device; barrier + sync on both sides."""
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
+    e0.record()
+    for i in range(steps):
+      fn(i)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)), ctx.launch_count - l0
+
+  result = {}
+  clocks = {}
+
+  # ---------------- flow ----------------
+  if args.path in ('both', 'flow'):
+    npairs_tiles = 6  # 6 x (2 x 16.8 MB) = 201 MB of distinct inputs > 126 MB L2
+    tiles = synth_tile_pairs(npairs_tiles, FLOW_TILE, 100 + rank, dev)
+    calc = flow_field.JAXMaskedXCorrWithStatsCalculator()
+    g = (FLOW_TILE - (PATCH - STEP)) // STEP
+    oyx = np.array(np.where(np.ones((g, g), bool))).T
+    job = flow_field._FlowJob(ctx, oyx, (FLOW_TILE,) * 2, (FLOW_TILE,) * 2,
+                              (PATCH,) * 2, (PATCH,) * 2, (STEP,) * 2, BATCH)
+    out_d = torch.empty((len(job.batches), BATCH, 4), dtype=torch.float32, device=dev)
+
+    def flow_step(i):
+      pre, post, _ = tiles[i % npairs_tiles]
+      job.run(pre, post, out=out_d)
+
+    for i in range(W):
+      flow_step(i)
+    with ClockSampler(local) as cs:
+      ms, launches = timed(flow_step, K)
+    clocks['flow'] = cs.summary()
+    pairs_per_step = g * g
+    flow_value = world * pairs_per_step * K / (ms * 1e-3)
+
+    # parity spot check of the timed configuration: the known shift is recovered.
+    pk = out_d.cpu().numpy()
+    dy, dx = tiles[(K - 1) % npairs_tiles][2]
+    flat = pk.reshape(-1, 4)[:pairs_per_step]
+    assert np.all(flat[:, 0] == dx) and np.all(flat[:, 1] == dy), 'flow parity'
+
+    # per-kernel durations (separate pass, CUDA events on the launching stream)
+    ctx.set_timing(True)
+    flow_step(0)
+    rep = ctx.timing_report()
+    ctx.set_timing(False)
+    kern_ms = {k: v['ms'] for k, v in rep.items() if k.startswith('flow_')}
+    tot_ms = sum(kern_ms.values())
+    dom = max(kern_ms, key=kern_ms.get)
+    achieved_tf = pairs_per_step * DENSE_FLOP_PER_PAIR / (tot_ms * 1e-3) / 1e12
+
+    # e2e: public API with pinned host arrays.
+    host = []
+    for pre, post, _ in tiles[:3]:
+      hp = torch.empty(pre.shape, dtype=torch.uint8, pin_memory=True)
+      hq = torch.empty(post.shape, dtype=torch.uint8, pin_memory=True)
+      hp.copy_(pre)
+      hq.copy_(post)
+      host.append((hp.numpy(), hq.numpy()))
+    torch.cuda.synchronize()
+
+    def flow_e2e(i):
+      a, b = host[i % len(host)]
+      out = calc.flow_field(a, b, PATCH, STEP, batch_size=BATCH)
+      assert out.shape == (4, g, g)
+
+    flow_e2e(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+      flow_e2e(i)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    result.update({
+        'metric': 'patch-pairs/s', 'value': flow_value, 'unit': 'patch-pairs/s',
+        'ms_per_step': ms / K, 'gpu_launches': launches,
+        'roofline': {
+            'bound': 'tensor', 'achieved': achieved_tf, 'peak': peaks['tflops'],
+            'unit': 'TFLOP/s', 'frac': achieved_tf / peaks['tflops'], 'traffic': None,
+            'peak_source': peaks['source'] + ', bf16 sustained',
+            'note': 'dense-equivalent: 2*160^4 FLOP per patch pair (SURVEY 8d) over '
+                    'the summed device time of the flow kernels of one step; the work '
+                    'is executed as fp32 FFTs on the CUDA cores (~13 MFLOP/pair), '
+                    'see DESIGN.md',
+            'dominant_kernel': dom, 'kernel_ms_per_step': kern_ms},
+        'e2e': {'value': world * pairs_per_step * K / (e2e_ms * 1e-3),
+                'unit': 'patch-pairs/s',
+                'h2d_bytes_per_step': 2 * FLOW_TILE * FLOW_TILE + int(job.starts_d.numel()) * 4,
+                'd2h_bytes_per_step': int(out_d.numel()) * 4},
+    })
+    del tiles, host
+
+  # ---------------- mesh ----------------
+  if args.path in ('both', 'mesh'):
+    iters = args.mesh_iters
+    cfg = mesh_config(mesh, iters)
+    prev = synth_mesh(MESH_N, 7 + rank, dev)
+    x0 = torch.zeros_like(prev)
+    chunk = mesh._Chunk(x0, None, prev, cfg, 0)
+    state = {'dt': cfg.dt, 'alpha': cfg.alpha, 'cap': cfg.start_cap}
+
+    def mesh_step(i):
+      dt, alpha, _, cap, _, _ = chunk.run(state['dt'], state['alpha'], state['cap'])
+      state.update(dt=float(dt), alpha=float(alpha), cap=float(cap))
+
+    for i in range(W):
+      mesh_step(i)
+    with ClockSampler(local) as cs:
+      ms, launches = timed(mesh_step, K)
+    clocks['mesh'] = cs.summary()
+    nodes = MESH_N * MESH_N
+    mesh_value = world * nodes * iters * K / (ms * 1e-3)
+
+    ctx.set_timing(True)
+    mesh_step(0)
+    rep = ctx.timing_report()
+    ctx.set_timing(False)
+    step_ms = rep['mesh_step']['ms'] / rep['mesh_step']['n']
+    achieved = nodes * MESH_BYTES_PER_UPDATE / (step_ms * 1e-3) / 1e9
+
+    hx = torch.zeros(x0.shape, dtype=torch.float32, pin_memory=True).numpy()
+    hp = torch.empty(prev.shape, dtype=torch.float32, pin_memory=True)
+    hp.copy_(prev)
+    hp = hp.numpy()
+    torch.cuda.synchronize()
+
+    def mesh_e2e(i):
+      out, e_kin, t = mesh.relax_mesh(hx, hp, cfg)
+      assert t == iters and out.shape == hx.shape
+
+    mesh_e2e(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+      mesh_e2e(i)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    result['mesh'] = {
+        'metric': 'node-updates/s', 'value': mesh_value, 'unit': 'node-updates/s',
+        'ms_per_step': ms / K, 'gpu_launches': launches,
+        'scaling': 'weak (replicas: one 2048^2 mesh per rank; the halo-sharded '
+                   'solver is not built yet)' if world > 1 else 'n/a',
+        'config': {'workload': f'mesh.relax_mesh chunk: {iters} FIRE steps, '
+                               f'[2,1,{MESH_N},{MESH_N}] fp32, k0=0.1, k=0.1, stride 40, '
+                               'prefer_orig_order, prev with 1% NaN; state 134 MB > L2'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
+                     'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                     'traffic': None, 'peak_source': peaks['source'],
+                     'kernel': 'mesh2d_kernel<1,true>',
+                     'kernel_us_per_launch': step_ms * 1e3,
+                     'algorithmic_bytes_per_launch': nodes * MESH_BYTES_PER_UPDATE},
+        'e2e': {'value': world * nodes * iters * K / (e2e_ms * 1e-3),
+                'unit': 'node-updates/s',
+                'h2d_bytes_per_step': 2 * 2 * nodes * 4,
+                'd2h_bytes_per_step': 2 * nodes * 4},
+    }
+
+  # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cores = len(os.sched_getaffinity(0))
+    if 'metric' in result:
+      v, n, s = time_cpu_flow(1536)
+      result['cpu_baseline'] = {
+          'value': v, 'unit': 'patch-pairs/s', 'cores': cores, 'kind': 'port',
+          'sample': f'one 1536^2 crop ({n} patch pairs, {s:.1f} s), '
+                    'oracle/flow_oracle.py on pocketfft fp32'}
+    if 'mesh' in result:
+      v, s, threads = time_cpu_mesh(MESH_N, 40)
+      result['mesh']['cpu_baseline'] = {
+          'value': v, 'unit': 'node-updates/s', 'cores': threads, 'kind': 'port',
+          'sample': f'40 FIRE steps on {MESH_N}^2 nodes ({s:.1f} s), '
+                    'oracle/mesh_oracle.c (OpenMP)'}
+
+  if rank == 0:
+    if 'metric' not in result:  # --path mesh: promote the mesh numbers
+      m = result.pop('mesh')
+      result.update(m)
+    line = {
+        'n_gpus': world, 'steps': K, 'warmup': W, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'flow_field on one {FLOW_TILE}x{FLOW_TILE} uint8 tile '
+                               f'pair per step, patch {PATCH}, step {STEP}, batch '
+                               f'{BATCH} (9801 patch pairs); inputs rotate over 6 tile '
+                               'pairs = 201 MB > L2',
+                   'per_rank': 'each rank processes its own tile pairs (no collective)'},
+        'clocks': clocks.get('flow', clocks.get('mesh')),
+        'clocks_mesh': clocks.get('mesh'),
+    }
+    if args.path == 'mesh':
+      line['config'] = result.pop('config')
+    line.update(result)
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+  ap.add_argument('--path', choices=['both', 'flow', 'mesh'], default='both')
+  ap.add_argument('--mesh-iters', type=int, default=1000)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.warmup < 3 and args.impl == 'ours':
+    args.warmup = max(args.warmup, 1)
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == '__main__':
+  main()

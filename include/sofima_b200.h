@@ -38,6 +38,11 @@ int sofima_ctx_destroy(sofima_ctx* ctx);
 int sofima_ctx_set_stream(sofima_ctx* ctx, void* stream);
 const char* sofima_last_error(const sofima_ctx* ctx); /* ctx may be NULL */
 int sofima_abi_version(void);
+/* Per-kernel timing (bench only): when on, every launch is bracketed by CUDA events
+ * on the context's stream; the report is a JSON object {"kernel": {"ms", "n"}}
+ * written to a host buffer, and clears the records. */
+int sofima_ctx_set_timing(sofima_ctx* ctx, int on);
+int sofima_ctx_timing_report(sofima_ctx* ctx, char* buf, int64_t buf_len);
 /* Number of kernel launches issued through `ctx` so far (bench "gpu_launches"). */
 int64_t sofima_ctx_launch_count(const sofima_ctx* ctx);
 

@@ -25,12 +25,15 @@ Test infrastructure only: never imported from `sofima_b200/`.
 from __future__ import annotations
 
 import collections.abc
+import os
 from typing import Sequence
 
 import numpy as np
 import scipy.fft
 
 F32 = np.float32
+# pocketfft worker threads (the CPU baseline uses every host core).
+WORKERS = int(os.environ.get('SOFIMA_ORACLE_FFT_WORKERS', os.cpu_count() or 1))
 
 
 def next_fast_len(n: int) -> int:
@@ -63,10 +66,12 @@ def masked_xcorr(prev, curr, prev_mask=None, curr_mask=None, dim=2):
   curr = curr[flip]
 
   def fwd(a):
-    return scipy.fft.rfftn(np.asarray(a, dtype=F32), s=fast_shape, axes=axes)
+    return scipy.fft.rfftn(np.asarray(a, dtype=F32), s=fast_shape, axes=axes,
+                           workers=WORKERS)
 
   def inv(a):
-    return scipy.fft.irfftn(a, s=fast_shape, axes=axes).astype(F32)
+    return scipy.fft.irfftn(a, s=fast_shape, axes=axes,
+                            workers=WORKERS).astype(F32)
 
   p_f = fwd(prev)
   c_f = fwd(curr)

@@ -140,6 +140,8 @@ _PROTOS = {
     'sofima_ctx_set_stream': (ctypes.c_int, [_vp, _vp]),
     'sofima_last_error': (ctypes.c_char_p, [_vp]),
     'sofima_ctx_launch_count': (ctypes.c_int64, [_vp]),
+    'sofima_ctx_set_timing': (ctypes.c_int, [_vp, ctypes.c_int]),
+    'sofima_ctx_timing_report': (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     'sofima_mesh_force': (ctypes.c_int, [
         _vp, ctypes.c_int, _vp, ctypes.POINTER(MeshShape), ctypes.c_double,
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, _vp]),
@@ -246,6 +248,15 @@ class Context:
   def bind_stream(self):
     stream = self._torch.cuda.current_stream(self.device).cuda_stream
     check(self.handle, lib().sofima_ctx_set_stream(self.handle, _vp(stream)))
+
+  def set_timing(self, on: bool):
+    check(self.handle, lib().sofima_ctx_set_timing(self.handle, int(on)))
+
+  def timing_report(self) -> dict:
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(self.handle, lib().sofima_ctx_timing_report(self.handle, buf, len(buf)))
+    return json.loads(buf.value.decode())
 
   @property
   def launch_count(self) -> int:

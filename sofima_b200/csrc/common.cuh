@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/sofima_b200.h"
 
@@ -27,6 +28,13 @@ struct sofima_ctx {
   std::map<std::string, Buf> scratch;
   void* pinned = nullptr;  // small pinned host block for scalar read-back
   size_t pinned_bytes = 0;
+  // Optional per-kernel timing with CUDA events on the launching stream (bench).
+  bool timing = false;
+  struct Rec {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Rec> recs;
 };
 
 namespace sofima {
@@ -80,6 +88,25 @@ inline int scratch(sofima_ctx* ctx, const char* name, size_t bytes, void** out) 
   *out = b.ptr;
   return SOFIMA_OK;
 }
+
+// RAII: brackets one kernel launch with events when ctx->timing is on.
+struct LaunchTimer {
+  sofima_ctx* ctx;
+  sofima_ctx::Rec rec;
+  bool on;
+  LaunchTimer(sofima_ctx* c, const char* name) : ctx(c), on(c->timing) {
+    if (!on) return;
+    rec.name = name;
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    cudaEventRecord(rec.e0, ctx->stream);
+  }
+  ~LaunchTimer() {
+    if (!on) return;
+    cudaEventRecord(rec.e1, ctx->stream);
+    ctx->recs.push_back(rec);
+  }
+};
 
 struct DeviceGuard {
   int prev = -1;

@@ -66,6 +66,43 @@ const char* sofima_last_error(const sofima_ctx* ctx) {
   return ctx ? ctx->err : sofima::g_last_error;
 }
 
+int sofima_ctx_set_timing(sofima_ctx* ctx, int on) {
+  if (!ctx) return sofima::fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
+  ctx->timing = on != 0;
+  return SOFIMA_OK;
+}
+
+int sofima_ctx_timing_report(sofima_ctx* ctx, char* buf, int64_t buf_len) {
+  if (!ctx || !buf || buf_len < 2) return sofima::fail(ctx, SOFIMA_EINVAL, "bad arguments");
+  sofima::DeviceGuard guard(ctx->device);
+  SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::map<std::string, std::pair<double, long long>> tot;
+  for (auto& r : ctx->recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& t = tot[r.name];
+    t.first += ms;
+    t.second += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->recs.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : tot) {
+    char item[256];
+    snprintf(item, sizeof(item), "%s\"%s\": {\"ms\": %.6f, \"n\": %lld}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.first, kv.second.second);
+    out += item;
+    first = false;
+  }
+  out += "}";
+  if ((int64_t)out.size() + 1 > buf_len)
+    return sofima::fail(ctx, SOFIMA_EINVAL, "timing report buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return SOFIMA_OK;
+}
+
 int64_t sofima_ctx_launch_count(const sofima_ctx* ctx) {
   return ctx ? ctx->launches : 0;
 }

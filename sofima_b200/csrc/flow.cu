@@ -670,15 +670,21 @@ static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const Pe
   const size_t words = (size_t)((n + 31) / 32);
   if ((rc = scratch(ctx, "flow.bitmap", sizeof(unsigned) * words, &bm))) return rc;
   SOFIMA_CUDA(ctx, cudaMemsetAsync(bm, 0, sizeof(unsigned) * words, ctx->stream));
-  peak1_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (float*)v1, (int*)p1);
-  SOFIMA_CHECK_LAUNCH(ctx);
+  {
+    LaunchTimer timer(ctx, "flow_peak1");
+    peak1_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (float*)v1, (int*)p1);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
   mark_peaks_kernel<<<(unsigned)ceil_div<long long>(B, 256), 256, 0, ctx->stream>>>(
       (const int*)p1, B, (unsigned*)bm);
   SOFIMA_CHECK_LAUNCH(ctx);
-  peak2_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (const float*)v1,
-                                                          (const int*)p1, (const unsigned*)bm,
-                                                          4, out_peaks);
-  SOFIMA_CHECK_LAUNCH(ctx);
+  {
+    LaunchTimer timer(ctx, "flow_peak2");
+    peak2_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (const float*)v1,
+                                                            (const int*)p1, (const unsigned*)bm,
+                                                            4, out_peaks);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
   return SOFIMA_OK;
 }
 
@@ -811,16 +817,25 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
     const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
     P.b0 = b0;
     P.nb = nb;
-    patch_mean_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, p->has_mean, p->mean,
-                                                                 (float*)means);
-    SOFIMA_CHECK_LAUNCH(ctx);
+    {
+      LaunchTimer timer(ctx, "flow_mean");
+      patch_mean_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, p->has_mean, p->mean,
+                                                                   (float*)means);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
     const int rp_max = (P.PY + 1) / 2;
-    rows_fwd_kernel<<<dim3(ceil_div(rp_max, R), P.nslots, nb), kThreads, smem_rows,
-                      ctx->stream>>>(P, Fx, R, (float2*)Tbuf);
-    SOFIMA_CHECK_LAUNCH(ctx);
-    cols_kernel<<<dim3(ceil_div(P.nkx, C), nb), kThreads, smem_cols, ctx->stream>>>(
-        P, Fy, C, pr, (const float2*)Tbuf, (float2*)Ubuf);
-    SOFIMA_CHECK_LAUNCH(ctx);
+    {
+      LaunchTimer timer(ctx, "flow_rows_fwd");
+      rows_fwd_kernel<<<dim3(ceil_div(rp_max, R), P.nslots, nb), kThreads, smem_rows,
+                        ctx->stream>>>(P, Fx, R, (float2*)Tbuf);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    {
+      LaunchTimer timer(ctx, "flow_cols");
+      cols_kernel<<<dim3(ceil_div(P.nkx, C), nb), kThreads, smem_cols, ctx->stream>>>(
+          P, Fy, C, pr, (const float2*)Tbuf, (float2*)Ubuf);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
     Outputs outs;
     memset(&outs, 0, sizeof(outs));
     if (!masked) {
@@ -836,23 +851,32 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       outs.dst[4] = loc + 1 * nsub * img_elems - b0 * img_elems;  // p_sq
       outs.dst[5] = loc + 2 * nsub * img_elems - b0 * img_elems;  // c_sq
     }
-    rows_inv_kernel<<<dim3(ceil_div((P.sy + 1) / 2, R), pr.nout, nb), kThreads, smem_rows,
-                      ctx->stream>>>(P, Fx, R, (const float2*)Ubuf, outs, scale);
-    SOFIMA_CHECK_LAUNCH(ctx);
+    {
+      LaunchTimer timer(ctx, "flow_rows_inv");
+      rows_inv_kernel<<<dim3(ceil_div((P.sy + 1) / 2, R), pr.nout, nb), kThreads, smem_rows,
+                        ctx->stream>>>(P, Fx, R, (const float2*)Ubuf, outs, scale);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
     if (masked) {
       const long long n = (long long)nb * img_elems;
       const size_t off = (size_t)b0 * img_elems;
       float* loc = static_cast<float*>(m6);
-      padfield_terms_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
-          images + off, ov_all + off, den_all + off, loc, loc + nsub * img_elems,
-          loc + 2 * nsub * img_elems, n, (float*)maxima);
-      SOFIMA_CHECK_LAUNCH(ctx);
+      {
+        LaunchTimer timer(ctx, "flow_padfield_terms");
+        padfield_terms_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+            images + off, ov_all + off, den_all + off, loc, loc + nsub * img_elems,
+            loc + 2 * nsub * img_elems, n, (float*)maxima);
+        SOFIMA_CHECK_LAUNCH(ctx);
+      }
     }
   }
   if (masked) {
-    padfield_normalise_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
-        images, ov_all, den_all, (long long)B * img_elems, (const float*)maxima);
-    SOFIMA_CHECK_LAUNCH(ctx);
+    {
+      LaunchTimer timer(ctx, "flow_padfield_norm");
+      padfield_normalise_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+          images, ov_all, den_all, (long long)B * img_elems, (const float*)maxima);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
   }
   return SOFIMA_OK;
 }

@@ -351,75 +351,107 @@ class JAXMaskedXCorrWithStatsCalculator:
       return output
 
     ctx = _native.Context.get()
-    torch = _torch()
-    dev = torch.device('cuda', ctx.device)
     pre_d = _device_image(pre_image, ctx)
     post_d = _device_image(post_image, ctx)
     pre_m = _device_mask(pre_mask, ctx)
     post_m = _device_mask(post_mask, ctx)
-    params, pre_d, post_d = _params(
-        nd, pre_d, post_d, pre_m, post_m, patch_size, post_patch_size, self._mean,
-        self._min_distance, 0.5, self._peak_radius)
+    job = _FlowJob(ctx, oyx, pre_image.shape, post_image.shape, patch_size,
+                   post_patch_size, step, batch_size, pre_targeting_field,
+                   pre_targeting_step, post_targeting_field, post_targeting_step)
+    peaks_d = job.run(pre_d, post_d, pre_m, post_m, self._mean, self._min_distance,
+                      self._peak_radius, progress_fn)
+    job.scatter(peaks_d.cpu().numpy(), output)
+    logging.info('Flow field estimation complete.')
+    return output
 
+
+class _FlowJob:
+  """Host-side index tables of one flow_field call, uploaded once.
+
+  Holds the per-batch patch start coordinates (flow_field.py:610-680: fixed batch
+  size with 'edge' padding, pre/post targeting offsets, clipping) on the device.
+  `run` queues one `sofima_xcorr_peaks` call per reference batch -- the
+  second-peak rule couples the members of a batch, so the batch composition is
+  part of the result -- without any host synchronisation in between.
+  """
+
+  def __init__(self, ctx, oyx, pre_shape, post_shape, patch_size, post_patch_size,
+               step, batch_size, pre_targeting_field=None, pre_targeting_step=None,
+               post_targeting_field=None, post_targeting_step=None):
+    torch = _torch()
+    self.ctx = ctx
+    self.nd = nd = len(pre_shape)
+    self.patch_size, self.post_patch_size = tuple(patch_size), tuple(post_patch_size)
+    self.batch_size = int(batch_size)
     patch_offset = ((np.array(patch_size) - post_patch_size) // 2)[None, ...]
     patch_offset = patch_offset.astype(int)
     step_arr = np.array(step).reshape((1, -1))
 
-    batches = list(_batches(oyx, batch_size))
-    pre_all, post_all, tg_all, po_all = [], [], [], []
-    for pos_zyx in batches:
+    self.batches = list(_batches(oyx, self.batch_size))
+    pre_all, post_all, self.tg_all, self.po_all = [], [], [], []
+    for pos_zyx in self.batches:
       real = pos_zyx.shape[0]
-      if real < batch_size:  # fixed batch size, 'edge' padding (flow_field.py:614)
-        proc = np.pad(pos_zyx, ((0, batch_size - real), (0, 0)), mode='edge')
+      if real < self.batch_size:  # 'edge' padding, flow_field.py:614-618
+        proc = np.pad(pos_zyx, ((0, self.batch_size - real), (0, 0)), mode='edge')
       else:
         proc = pos_zyx
       post_starts = proc * step_arr
       pre_starts = np.clip(post_starts - patch_offset, 0, np.inf).astype(int)
-
       tg = po = None
       if pre_targeting_field is not None and pre_targeting_step is not None:
         tg = _targeting_offsets(pre_targeting_field, pre_targeting_step,
-                                pre_starts, patch_size, pre_image.shape)
+                                pre_starts, patch_size, pre_shape)
         pre_starts = pre_starts + tg
       if post_targeting_field is not None and post_targeting_step is not None:
         po = _targeting_offsets(post_targeting_field, post_targeting_step,
-                                post_starts, post_patch_size, post_image.shape)
+                                post_starts, post_patch_size, post_shape)
         post_starts = post_starts + po
       pre_all.append(np.clip(pre_starts, 0, np.inf).astype(np.int32))
       post_all.append(np.clip(post_starts, 0, np.inf).astype(np.int32))
-      tg_all.append(tg)
-      po_all.append(po)
+      self.tg_all.append(tg)
+      self.po_all.append(po)
 
-    # One upload of every start coordinate, one launch sequence per reference
-    # batch (the second-peak rule couples the members of a batch), one download.
-    nb = len(batches)
     # NB: np.stack keeps the (Fortran) layout of np.where-derived views, and the
     # library takes plain C-contiguous [batch, nd] tables.
     starts_h = np.ascontiguousarray(
         np.stack([np.stack(pre_all), np.stack(post_all)]), dtype=np.int32)
-    starts_d = torch.from_numpy(starts_h).to(dev).contiguous()  # [2, nb, batch, nd]
-    peaks_d = torch.empty((nb, batch_size, nd + 2), dtype=torch.float32, device=dev)
-    ctx.bind_stream()
+    dev = torch.device('cuda', ctx.device)
+    self.starts_d = torch.from_numpy(starts_h).to(dev).contiguous()  # [2, nb, B, nd]
+    self.num_pairs = int(oyx.shape[0])
+
+  def run(self, pre_d, post_d, pre_m=None, post_m=None, mean=None, min_distance=2,
+          peak_radius=5, progress_fn=_silent_fn, out=None):
+    """Queues every batch on the current stream; returns peaks [nb, B, nd + 2]."""
+    torch = _torch()
+    nb = len(self.batches)
+    params, pre_d, post_d = _params(
+        self.nd, pre_d, post_d, pre_m, post_m, self.patch_size, self.post_patch_size,
+        mean, min_distance, 0.5, peak_radius)
+    if out is None:
+      out = torch.empty((nb, self.batch_size, self.nd + 2), dtype=torch.float32,
+                        device=pre_d.device)
+    self.ctx.bind_stream()
     lib = _native.lib()
     for i in progress_fn(list(range(nb))):
       rc = lib.sofima_xcorr_peaks(
-          ctx.handle, ctypes.byref(params), pre_d.data_ptr(), post_d.data_ptr(),
-          _ptr(pre_m), _ptr(post_m), starts_d[0, i].data_ptr(),
-          starts_d[1, i].data_ptr(), batch_size, peaks_d[i].data_ptr())
-      _native.check(ctx.handle, rc)
-    peaks = peaks_d.cpu().numpy()
+          self.ctx.handle, ctypes.byref(params), pre_d.data_ptr(), post_d.data_ptr(),
+          _ptr(pre_m), _ptr(post_m), self.starts_d[0, i].data_ptr(),
+          self.starts_d[1, i].data_ptr(), self.batch_size, out[i].data_ptr())
+      _native.check(self.ctx.handle, rc)
+    return out
 
-    for i, pos_zyx in enumerate(batches):
+  def scatter(self, peaks: np.ndarray, output: np.ndarray):
+    """Adds the targeting offsets back and writes rows into the flow field
+    (flow_field.py:699-709)."""
+    nd = self.nd
+    for i, pos_zyx in enumerate(self.batches):
       real = pos_zyx.shape[0]
       v = peaks[i, :real]
-      if tg_all[i] is not None:
-        v[:, :nd] = v[:, :nd] + tg_all[i][:real, ::-1]  # xy[z]
-      if po_all[i] is not None:
-        v[:, :nd] = v[:, :nd] - po_all[i][:real, ::-1]  # xy[z]
+      if self.tg_all[i] is not None:
+        v[:, :nd] = v[:, :nd] + self.tg_all[i][:real, ::-1]  # xy[z]
+      if self.po_all[i] is not None:
+        v[:, :nd] = v[:, :nd] - self.po_all[i][:real, ::-1]  # xy[z]
       output[(slice(None),) + tuple(pos_zyx.T)] = v.T
-
-    logging.info('Flow field estimation complete.')
-    return output
 
 
 def _targeting_offsets(field, tg_step, starts, patch, img_shape):
