@@ -178,6 +178,7 @@ __device__ __forceinline__ float load_px(const void* data, int dtype, long long 
 }
 
 // Per-patch mean (flow_field.py:340-353): masked mean over the unmasked pixels.
+// One block per (pair, image); warps stride the rows, lanes stride the columns.
 __global__ void __launch_bounds__(kThreads)
 patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
   const int which = blockIdx.y;
@@ -194,19 +195,28 @@ patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
     my0 = clamp_start(P.starts[which][b * 2 + 0], I.ph, I.mh);
     mx0 = clamp_start(P.starts[which][b * 2 + 1], I.pw, I.mw);
   }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sum = 0.0;
-  unsigned long long isum = 0;
+  unsigned int isum = 0;  // <= 255 * rows * ceil(cols / 32) per thread: no overflow
   int cnt = 0;
-  const int n = I.ph * I.pw;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
-    const int y = i / I.pw, x = i - y * I.pw;
-    bool valid = true;
-    if (I.mask) valid = I.mask[(long long)(my0 + y) * I.mw + mx0 + x] == 0;
-    if (!valid) continue;
-    const long long gi = (long long)(y0 + y) * I.w + x0 + x;
-    if (P.dtype == SOFIMA_U8) isum += static_cast<const uint8_t*>(I.data)[gi];
-    else sum += (double)static_cast<const float*>(I.data)[gi];
-    ++cnt;
+  for (int y = warp; y < I.ph; y += kThreads / 32) {
+    const long long row = (long long)(y0 + y) * I.w + x0;
+    const uint8_t* mrow = I.mask ? I.mask + (long long)(my0 + y) * I.mw + mx0 : nullptr;
+    if (P.dtype == SOFIMA_U8) {
+      const uint8_t* src = static_cast<const uint8_t*>(I.data) + row;
+      for (int x = lane; x < I.pw; x += 32) {
+        const bool valid = mrow ? (mrow[x] == 0) : true;
+        isum += valid ? (unsigned)src[x] : 0u;
+        cnt += valid;
+      }
+    } else {
+      const float* src = static_cast<const float*>(I.data) + row;
+      for (int x = lane; x < I.pw; x += 32) {
+        const bool valid = mrow ? (mrow[x] == 0) : true;
+        sum += valid ? (double)src[x] : 0.0;
+        cnt += valid;
+      }
+    }
   }
   if (P.dtype == SOFIMA_U8) sum = (double)isum;
   __shared__ double rs[kThreads / 32];
@@ -216,13 +226,13 @@ patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = sum; rc[threadIdx.x >> 5] = cnt; }
+  if (lane == 0) { rs[warp] = sum; rc[warp] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0; int c = 0;
-    for (int w = 0; w < kThreads / 32; ++w) { s += rs[w]; c += rc[w]; }
+    double t = 0.0; int c = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { t += rs[w]; c += rc[w]; }
     // fp32 sum / fp32 count, as jnp.mean / jnp.nanmean (0/0 -> NaN).
-    means_out[b * 2 + which] = __fdiv_rn((float)s, (float)c);
+    means_out[b * 2 + which] = __fdiv_rn((float)t, (float)c);
   }
 }
 
@@ -485,9 +495,11 @@ __device__ unsigned long long block_max_key(unsigned long long k, unsigned long 
   return r;
 }
 
-// Pass 1: global max / first argmax per image.  peak1[b] = {value or -inf, index}.
+// Pass 1 (generic path; the fast path folds this into rows_inv_fast): global max and
+// first argmax per image as an order-preserving key, plus a NaN flag.
 __global__ void __launch_bounds__(kThreads)
-peak1_kernel(const float* __restrict__ img, PeakParams pp, float* v1, int* p1) {
+peak1_kernel(const float* __restrict__ img, PeakParams pp, unsigned long long* keys,
+             int* nanflag) {
   __shared__ unsigned long long sm[kThreads / 32];
   __shared__ int nan_flag;
   if (threadIdx.x == 0) nan_flag = 0;
@@ -505,19 +517,26 @@ peak1_kernel(const float* __restrict__ img, PeakParams pp, float* v1, int* p1) {
   if (has_nan) nan_flag = 1;
   best = block_max_key(best, sm);
   if (threadIdx.x == 0) {
-    float v; unsigned idx;
-    key_decode(best, &v, &idx);
-    // The global maximum is a peak iff it is > 0 (it always equals its own
-    // zero-padded neighbourhood maximum and must exceed threshold_rel * max).
-    const bool ok = !nan_flag && n > 0 && (v > pp.thr_rel * v);
-    v1[blockIdx.x] = ok ? v : -INFINITY;
-    p1[blockIdx.x] = ok ? (int)idx : 0;  // argmax of an all -inf row is 0
+    keys[blockIdx.x] = best;
+    nanflag[blockIdx.x] = nan_flag;
   }
 }
 
-__global__ void mark_peaks_kernel(const int* p1, long long B, unsigned* bitmap) {
+// Decodes the keys into (v1, p1) and marks every first peak in the batch bitmap.
+__global__ void peak1_decode_kernel(const unsigned long long* keys, const int* nanflag,
+                                    long long B, PeakParams pp, float* v1, int* p1,
+                                    unsigned* bitmap) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) atomicOr(&bitmap[p1[b] >> 5], 1u << (p1[b] & 31));
+  if (b >= B) return;
+  float v = -INFINITY;
+  unsigned idx = 0;
+  if (keys[b] != 0) key_decode(keys[b], &v, &idx);
+  // The global maximum is a peak iff it exceeds threshold_rel * max (it always
+  // equals its own zero-padded neighbourhood maximum), i.e. iff it is > 0.
+  const bool ok = !nanflag[b] && keys[b] != 0 && (v > pp.thr_rel * v);
+  v1[b] = ok ? v : -INFINITY;
+  p1[b] = ok ? (int)idx : 0;  // argmax of an all -inf row is 0
+  atomicOr(&bitmap[p1[b] >> 5], 1u << (p1[b] & 31));
 }
 
 __device__ __forceinline__ bool is_peak(const float* im, const PeakParams& pp, int y, int x,
@@ -600,6 +619,14 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
   }
 }
 
+}  // namespace flow
+}  // namespace sofima
+
+#include "flow_fast.cuh"
+
+namespace sofima {
+namespace flow {
+
 // ---------------------------------------------------------------------------------
 // Host side.
 // ---------------------------------------------------------------------------------
@@ -657,26 +684,33 @@ static int make_plan(sofima_ctx* ctx, int L, FftPlan* P) {
   return SOFIMA_OK;
 }
 
+// keys_ready: the (max, argmax) keys and NaN flags of the batch were already
+// produced by rows_inv_fast into the "flow.keys" / "flow.nan" scratch buffers.
 static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const PeakParams& pp,
-                     float* out_peaks) {
+                     float* out_peaks, bool keys_ready) {
   if (B == 0) return SOFIMA_OK;
   const long long n = (long long)pp.sy * pp.sx;
   if (2 * pp.ry + 1 > pp.sy || 2 * pp.rx + 1 > pp.sx)
     return fail(ctx, SOFIMA_EINVAL, "peak_radius window larger than the correlation image");
-  void *v1 = nullptr, *p1 = nullptr, *bm = nullptr;
+  void *v1 = nullptr, *p1 = nullptr, *bm = nullptr, *keys = nullptr, *nanf = nullptr;
   int rc;
   if ((rc = scratch(ctx, "flow.v1", sizeof(float) * B, &v1))) return rc;
   if ((rc = scratch(ctx, "flow.p1", sizeof(int) * B, &p1))) return rc;
+  if ((rc = scratch(ctx, "flow.keys", sizeof(unsigned long long) * B, &keys))) return rc;
+  if ((rc = scratch(ctx, "flow.nan", sizeof(int) * B, &nanf))) return rc;
   const size_t words = (size_t)((n + 31) / 32);
   if ((rc = scratch(ctx, "flow.bitmap", sizeof(unsigned) * words, &bm))) return rc;
   SOFIMA_CUDA(ctx, cudaMemsetAsync(bm, 0, sizeof(unsigned) * words, ctx->stream));
-  {
+  if (!keys_ready) {
     LaunchTimer timer(ctx, "flow_peak1");
-    peak1_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (float*)v1, (int*)p1);
+    peak1_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp,
+                                                            (unsigned long long*)keys,
+                                                            (int*)nanf);
     SOFIMA_CHECK_LAUNCH(ctx);
   }
-  mark_peaks_kernel<<<(unsigned)ceil_div<long long>(B, 256), 256, 0, ctx->stream>>>(
-      (const int*)p1, B, (unsigned*)bm);
+  peak1_decode_kernel<<<(unsigned)ceil_div<long long>(B, 256), 256, 0, ctx->stream>>>(
+      (const unsigned long long*)keys, (const int*)nanf, B, pp, (float*)v1, (int*)p1,
+      (unsigned*)bm);
   SOFIMA_CHECK_LAUNCH(ctx);
   {
     LaunchTimer timer(ctx, "flow_peak2");
@@ -707,12 +741,66 @@ static int check_params(sofima_ctx* ctx, const sofima_xcorr_params* p) {
   return SOFIMA_OK;
 }
 
+// ---- fast path (flow_fast.cuh): unmasked, both FFT lengths of the form 16 * N2 ----
+static bool fast_n2(int L, int* n2) {
+  if (L % kN1) return false;
+  const int v = L / kN1;
+  for (int ok : {8, 10, 12, 15, 16, 20, 24, 25, 32})
+    if (v == ok) { *n2 = v; return true; }
+  return false;
+}
+
+// Transforms per block (row pairs resp. spectral columns): 8, or 4 for the long
+// transforms so that the exchange buffers stay below the 48 KB static limit.
+template <int N2>
+struct FastLines {
+  static constexpr int n = N2 <= 20 ? 8 : 4;
+};
+
+template <int N2>
+static void launch_rows_fwd_fast(sofima_ctx* ctx, const Problem& P, const float2* tw, float2* T,
+                                 int rp_max) {
+  constexpr int TR = FastLines<N2>::n;
+  rows_fwd_fast<N2, TR><<<dim3(ceil_div(rp_max, TR), P.nslots, P.nb), TR * FastDims<N2>::G, 0,
+                         ctx->stream>>>(P, tw, T);
+}
+template <int N2>
+static void launch_cols_fast(sofima_ctx* ctx, const Problem& P, const float2* tw, const float2* T,
+                             float2* U) {
+  constexpr int C = FastLines<N2>::n;
+  cols_fast<N2, C><<<dim3(ceil_div(P.nkx, C), P.nb), C * FastDims<N2>::G, 0, ctx->stream>>>(
+      P, tw, T, U);
+}
+template <int N2>
+static void launch_rows_inv_fast(sofima_ctx* ctx, const Problem& P, const float2* tw,
+                                 const float2* U, float* images, float scale,
+                                 unsigned long long* keys, int* nanflag) {
+  constexpr int TR = FastLines<N2>::n;
+  rows_inv_fast<N2, TR><<<dim3(ceil_div((P.sy + 1) / 2, TR), 1, P.nb), TR * FastDims<N2>::G, 0,
+                         ctx->stream>>>(P, tw, U, images, scale, keys, nanflag);
+}
+
+#define SOFIMA_N2_SWITCH(n2, CALL)          \
+  switch (n2) {                             \
+    case 8: CALL(8); break;                 \
+    case 10: CALL(10); break;               \
+    case 12: CALL(12); break;               \
+    case 15: CALL(15); break;               \
+    case 16: CALL(16); break;               \
+    case 20: CALL(20); break;               \
+    case 24: CALL(24); break;               \
+    case 25: CALL(25); break;               \
+    case 32: CALL(32); break;               \
+    default: break;                         \
+  }
+
 // Computes the correlation images of one batch into `images` [B][sy][sx].
 static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
                      const void* post_img, const uint8_t* pre_mask, const uint8_t* post_mask,
                      const int32_t* pre_starts, const int32_t* post_starts, long long B,
-                     float* images) {
+                     float* images, bool* keys_ready) {
   const bool masked = pre_mask != nullptr || post_mask != nullptr;
+  if (keys_ready) *keys_ready = false;
   Problem P;
   memset(&P, 0, sizeof(P));
   P.dtype = p->img_dtype;
@@ -762,6 +850,17 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   int rc;
   if ((rc = make_plan(ctx, Lx, &Fx))) return rc;
   if ((rc = make_plan(ctx, Ly, &Fy))) return rc;
+
+  int n2x = 0, n2y = 0;
+  const bool fast = !masked && fast_n2(Lx, &n2x) && fast_n2(Ly, &n2y);
+  void *keys = nullptr, *nanf = nullptr;
+  if (fast && keys_ready) {
+    if ((rc = scratch(ctx, "flow.keys", sizeof(unsigned long long) * B, &keys))) return rc;
+    if ((rc = scratch(ctx, "flow.nan", sizeof(int) * B, &nanf))) return rc;
+    SOFIMA_CUDA(ctx, cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * B, ctx->stream));
+    SOFIMA_CUDA(ctx, cudaMemsetAsync(nanf, 0, sizeof(int) * B, ctx->stream));
+    *keys_ready = true;
+  }
 
   // Shared-memory budgets.
   const size_t smem_cap = 200 * 1024;
@@ -824,6 +923,39 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       SOFIMA_CHECK_LAUNCH(ctx);
     }
     const int rp_max = (P.PY + 1) / 2;
+    if (fast) {
+      {
+        LaunchTimer timer(ctx, "flow_rows_fwd");
+#define CALL(N) launch_rows_fwd_fast<N>(ctx, P, Fx.tw, (float2*)Tbuf, rp_max)
+        SOFIMA_N2_SWITCH(n2x, CALL)
+#undef CALL
+        SOFIMA_CHECK_LAUNCH(ctx);
+      }
+      {
+        LaunchTimer timer(ctx, "flow_cols");
+#define CALL(N) launch_cols_fast<N>(ctx, P, Fy.tw, (const float2*)Tbuf, (float2*)Ubuf)
+        SOFIMA_N2_SWITCH(n2y, CALL)
+#undef CALL
+        SOFIMA_CHECK_LAUNCH(ctx);
+      }
+      {
+        LaunchTimer timer(ctx, "flow_rows_inv");
+        unsigned long long* kp = static_cast<unsigned long long*>(keys);
+        int* np = static_cast<int*>(nanf);
+        if (!kp) {  // caller does not want the fused peak search: throw-away slots
+          void* tmp = nullptr;
+          if ((rc = scratch(ctx, "flow.keys_tmp", (sizeof(unsigned long long) + sizeof(int)) * B,
+                            &tmp))) return rc;
+          kp = static_cast<unsigned long long*>(tmp);
+          np = reinterpret_cast<int*>(kp + B);
+        }
+#define CALL(N) launch_rows_inv_fast<N>(ctx, P, Fx.tw, (const float2*)Ubuf, images, scale, kp, np)
+        SOFIMA_N2_SWITCH(n2x, CALL)
+#undef CALL
+        SOFIMA_CHECK_LAUNCH(ctx);
+      }
+      continue;
+    }
     {
       LaunchTimer timer(ctx, "flow_rows_fwd");
       rows_fwd_kernel<<<dim3(ceil_div(rp_max, R), P.nslots, nb), kThreads, smem_rows,
@@ -900,7 +1032,7 @@ int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p, const voi
     return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
   DeviceGuard guard(ctx->device);
   return flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
-                         post_starts, batch, out_xcorr);
+                         post_starts, batch, out_xcorr, nullptr);
 }
 
 int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
@@ -921,8 +1053,9 @@ int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void
   void* images = nullptr;
   if ((rc = scratch(ctx, "flow.images", sizeof(float) * (size_t)batch * sy * sx, &images)))
     return rc;
+  bool keys_ready = false;
   rc = flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts, post_starts,
-                       batch, static_cast<float*>(images));
+                       batch, static_cast<float*>(images), &keys_ready);
   if (rc) return rc;
   flow::PeakParams pp;
   pp.sy = sy;
@@ -934,7 +1067,8 @@ int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void
   // center_offset = (pre + post) // 2 - 1, flow_field.py:357-360
   pp.cy = (p->pre_patch[0] + p->post_patch[0]) / 2 - 1;
   pp.cx = (p->pre_patch[1] + p->post_patch[1]) / 2 - 1;
-  return flow::run_peaks(ctx, static_cast<const float*>(images), batch, pp, out_peaks);
+  return flow::run_peaks(ctx, static_cast<const float*>(images), batch, pp, out_peaks,
+                         keys_ready);
 }
 
 int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img, const int64_t* img_shape,
@@ -960,7 +1094,7 @@ int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img, const int6
   pp.rx = peak_radius[1];
   pp.cy = center_offset[0];
   pp.cx = center_offset[1];
-  return flow::run_peaks(ctx, img, batch, pp, out_peaks);
+  return flow::run_peaks(ctx, img, batch, pp, out_peaks, false);
 }
 
 }  // extern "C"

@@ -1,0 +1,295 @@
+// Two-pass register-resident FFT kernels for the unmasked correlation path.
+//
+// For transform lengths L = 16 * N2 (N2 in {8,10,12,15,16,20,24,25,32}; L = 320 for
+// the EM default patch 160) each 1-d FFT is done in exactly two passes with all
+// butterflies in registers (generated codelets, fft_codelets.cuh):
+//
+//   forward  x[N2 n1 + n2] -> X[k1 + 16 k2]:
+//     pass 1  thread n2 : 16-point DFT over n1, twiddle W_L^(n2 k1)
+//     (exchange through shared memory, conflict-free padded layout)
+//     pass 2  thread k1 : N2-point DFT over n2
+//   inverse  X[k1 + 16 k2] -> x[N2 n1 + n2]  (re/im swap trick, same codelets):
+//     pass 1  thread k1 : N2-point DFT over k2, twiddle W_L^(k1 n2)
+//     pass 2  thread n2 : 16-point DFT over k1
+//
+// The three stages are those of flow.cu (rows_fwd / cols / rows_inv); the cols
+// stage keeps the spectrum of the first patch in shared memory, multiplies in
+// registers and runs the inverse without leaving the SM.  rows_inv also folds the
+// first peak search (global max + first argmax per image) into its epilogue.
+#pragma once
+
+#include "fft_codelets.cuh"
+
+namespace sofima {
+namespace flow {
+
+constexpr int kN1 = 16;
+
+template <int N2>
+struct FastDims {
+  static constexpr int L = kN1 * N2;
+  static constexpr int N2P = N2 | 1;           // odd pitch: conflict-free exchange
+  static constexpr int EX = kN1 * N2P + 2;     // float2 per exchange line (== 2 mod 16)
+  static constexpr int LP = L + 2;             // padded spectrum line (== 2 mod 16)
+  static constexpr int G = N2 > kN1 ? N2 : kN1;  // threads per transform
+};
+
+__device__ __forceinline__ float2 swap_ri(float2 a) { return make_float2(a.y, a.x); }
+
+// ---------------------------------------------------------------------------------
+// Stage 1: forward row FFTs (two real rows per complex transform).
+// grid = (row-pair groups, slot, pair), block = TR * N2 threads.
+// ---------------------------------------------------------------------------------
+template <int N2, int TR>
+__global__ void __launch_bounds__(TR * FastDims<N2>::G)
+rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) {
+  using D = FastDims<N2>;
+  constexpr int L = D::L;
+  __shared__ float2 ex[TR * D::EX];
+  __shared__ float2 xs[TR * L];
+  __shared__ float2 tw_s[L];
+  const Slot sl = P.slot[blockIdx.y];
+  const Image& I = P.img[sl.src];
+  const long long b = P.b0 + blockIdx.z;
+  const int rp0 = blockIdx.x * TR;
+  const int nrows = I.ph;
+  if (2 * rp0 >= nrows) return;
+  constexpr int NT = TR * D::G;
+  for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
+  __syncthreads();
+
+  const int y0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.w);
+  int my0 = 0, mx0 = 0;
+  if (I.mask) {
+    my0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.mh);
+    mx0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.mw);
+  }
+  const float mean = P.means[b * 2 + sl.src];
+  const bool flip = sl.src == 1;  // curr[::-1, ::-1], flow_field.py:78-79
+
+  auto sample = [&](int y, int x) -> float {
+    if (y >= nrows) return 0.f;
+    const int yy = flip ? I.ph - 1 - y : y, xx = flip ? I.pw - 1 - x : x;
+    bool valid = true;
+    if (I.mask) valid = I.mask[(long long)(my0 + yy) * I.mw + mx0 + xx] == 0;
+    if (sl.xform == 1) return valid ? 1.f : 0.f;
+    float v = load_px(I.data, P.dtype, (long long)(y0 + yy) * I.w + x0 + xx) - mean;
+    v = valid ? v : 0.f;  // where(mask, 0, patch - mean), flow_field.py:73-76
+    return sl.xform == 2 ? v * v : v;
+  };
+
+  if (threadIdx.x < TR * N2) {  // pass 1: thread (f, n2)
+    const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
+    const int y = 2 * (rp0 + f);
+    float2 a[kN1];
+#pragma unroll
+    for (int n1 = 0; n1 < kN1; ++n1) {
+      const int x = N2 * n1 + n2;
+      a[n1] = (x < I.pw && y < nrows) ? make_float2(sample(y, x), sample(y + 1, x))
+                                      : make_float2(0.f, 0.f);
+    }
+    Dft<kN1>::run(a);
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; ++k1)
+      ex[f * D::EX + k1 * D::N2P + n2] = cmul(a[k1], tw_s[n2 * k1]);
+  }
+  __syncthreads();
+  if (threadIdx.x < TR * kN1) {  // pass 2: thread (f, k1)
+    const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
+    float2 bq[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) bq[n2] = ex[f * D::EX + k1 * D::N2P + n2];
+    Dft<N2>::run(bq);
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) xs[f * L + k1 + kN1 * k2] = bq[k2];
+  }
+  __syncthreads();
+  // separate the two real rows: X_even = (Z[k] + conj Z[L-k]) / 2,
+  //                             X_odd  = (Z[k] - conj Z[L-k]) / (2i)
+  float2* Tb = T + ((size_t)blockIdx.y * P.nb + blockIdx.z) * P.PY * P.nkx;
+  for (int i = threadIdx.x; i < TR * P.nkx; i += NT) {
+    const int f = i / P.nkx, k = i - f * P.nkx;
+    const int y = 2 * (rp0 + f);
+    if (y >= nrows) continue;
+    const float2 a = xs[f * L + k];
+    const float2 c = xs[f * L + (k == 0 ? 0 : L - k)];
+    Tb[(size_t)y * P.nkx + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+    if (y + 1 < nrows)
+      Tb[(size_t)(y + 1) * P.nkx + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage 2: forward column FFTs of both patches, product, inverse column FFT.
+// grid = (column groups, pair), block = C * N2 threads (c fastest).
+// ---------------------------------------------------------------------------------
+template <int N2, int C>
+__global__ void __launch_bounds__(C * FastDims<N2>::G)
+cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T,
+          float2* __restrict__ U) {
+  using D = FastDims<N2>;
+  constexpr int L = D::L;
+  __shared__ float2 ex[C * D::EX];
+  __shared__ float2 sa[C * D::LP];
+  __shared__ float2 tw_s[L];
+  for (int i = threadIdx.x; i < L; i += C * D::G) tw_s[i] = __ldg(&tw[i]);
+  const int k0 = blockIdx.x * C;
+  const int c = threadIdx.x % C;
+  const int r = threadIdx.x / C;  // n2 in pass-1 role, k1 in pass-2 role (r < 16)
+  const bool col_ok = k0 + c < P.nkx;
+  float2 prod[N2];
+
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const int rows = P.img[sl].ph;
+    const float2* Tb = T + ((size_t)sl * P.nb + blockIdx.y) * P.PY * P.nkx + k0 + c;
+    __syncthreads();  // twiddles staged / previous readers of ex done
+    if (r < N2) {
+      float2 a[kN1];
+#pragma unroll
+      for (int n1 = 0; n1 < kN1; ++n1) {
+        const int y = N2 * n1 + r;
+        a[n1] = (col_ok && y < rows) ? Tb[(size_t)y * P.nkx] : make_float2(0.f, 0.f);
+      }
+      Dft<kN1>::run(a);
+#pragma unroll
+      for (int k1 = 0; k1 < kN1; ++k1)
+        ex[c * D::EX + k1 * D::N2P + r] = cmul(a[k1], tw_s[r * k1]);
+    }
+    __syncthreads();
+    if (r < kN1) {
+      float2 bq[N2];
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) bq[n2] = ex[c * D::EX + r * D::N2P + n2];
+      Dft<N2>::run(bq);
+      if (sl == 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) sa[c * D::LP + r + kN1 * k2] = bq[k2];
+      } else {
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2)
+          prod[k2] = swap_ri(cmul(bq[k2], sa[c * D::LP + r + kN1 * k2]));
+      }
+    }
+  }
+  // inverse: N2-point DFT over k2 (thread k1), twiddle, exchange, 16-point over k1.
+  __syncthreads();
+  if (r < kN1) {
+    Dft<N2>::run(prod);
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2)
+      ex[c * D::EX + r * D::N2P + n2] = cmul(prod[n2], tw_s[r * n2]);
+  }
+  __syncthreads();
+  if (r < N2) {
+    float2 a[kN1];
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; ++k1) a[k1] = ex[c * D::EX + k1 * D::N2P + r];
+    Dft<kN1>::run(a);
+    if (col_ok) {
+      float2* Ub = U + (size_t)blockIdx.y * P.sy * P.nkx + k0 + c;
+#pragma unroll
+      for (int n1 = 0; n1 < kN1; ++n1) {
+        const int y = N2 * n1 + r;
+        if (y < P.sy) Ub[(size_t)y * P.nkx] = swap_ri(a[n1]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage 3: inverse row FFTs, crop, scale, and the first-peak search.
+// grid = (row-pair groups, 1, pair), block = TR * N2 threads.
+// keys[pair]: running (max value, lowest flat index) of the image, nanflag[pair].
+// ---------------------------------------------------------------------------------
+template <int N2, int TR>
+__global__ void __launch_bounds__(TR * FastDims<N2>::G)
+rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ U,
+              float* __restrict__ images, float scale, unsigned long long* keys,
+              int* nanflag) {
+  using D = FastDims<N2>;
+  constexpr int L = D::L;
+  __shared__ float2 ex[TR * D::EX];
+  __shared__ float2 tw_s[L];
+  constexpr int NT = TR * D::G;
+  __shared__ unsigned long long kred[(NT + 31) / 32];
+  const int rp0 = blockIdx.x * TR;
+  if (2 * rp0 >= P.sy) return;
+  for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
+  const float2* Ub = U + (size_t)blockIdx.z * P.sy * P.nkx;
+  __syncthreads();
+  if (threadIdx.x < TR * kN1) {  // thread (f, k1)
+    const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
+    const int y = 2 * (rp0 + f);
+    float2 bq[N2];
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) {
+      const int k = k1 + kN1 * k2;
+      float2 z = make_float2(0.f, 0.f);
+      if (y < P.sy) {
+        const int kk = (k < P.nkx) ? k : L - k;
+        float2 u0 = Ub[(size_t)y * P.nkx + kk];
+        float2 u1 = (y + 1 < P.sy) ? Ub[(size_t)(y + 1) * P.nkx + kk] : make_float2(0.f, 0.f);
+        // c2r ignores the imaginary part of the DC and Nyquist bins.
+        if (kk == 0 || kk == L / 2) { u0.y = 0.f; u1.y = 0.f; }
+        if (k >= P.nkx) { u0.y = -u0.y; u1.y = -u1.y; }
+        z = make_float2(u0.x - u1.y, u0.y + u1.x);  // u0 + i u1
+      }
+      bq[k2] = swap_ri(z);
+    }
+    Dft<N2>::run(bq);
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2)
+      ex[f * D::EX + k1 * D::N2P + n2] = cmul(bq[n2], tw_s[k1 * n2]);
+  }
+  __syncthreads();
+  unsigned long long best = 0;
+  int has_nan = 0;
+  if (threadIdx.x < TR * N2) {  // thread (f, n2)
+    const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
+    const int y = 2 * (rp0 + f);
+    float2 a[kN1];
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; ++k1) a[k1] = ex[f * D::EX + k1 * D::N2P + n2];
+    Dft<kN1>::run(a);
+    if (y < P.sy) {
+      float* out = images + (size_t)(P.b0 + blockIdx.z) * P.sy * P.sx;
+#pragma unroll
+      for (int n1 = 0; n1 < kN1; ++n1) {
+        const int x = N2 * n1 + n2;
+        if (x >= P.sx) continue;
+        // after the re/im swap: real part -> row y, imaginary part -> row y + 1
+        const float v0 = a[n1].y * scale, v1 = a[n1].x * scale;
+        out[(size_t)y * P.sx + x] = v0;
+        if (v0 != v0) has_nan = 1;
+        unsigned long long kk = peak_key(v0, (unsigned)(y * P.sx + x));
+        best = kk > best ? kk : best;
+        if (y + 1 < P.sy) {
+          out[(size_t)(y + 1) * P.sx + x] = v1;
+          if (v1 != v1) has_nan = 1;
+          kk = peak_key(v1, (unsigned)((y + 1) * P.sx + x));
+          best = kk > best ? kk : best;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+    has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    kred[threadIdx.x >> 5] = best;
+    if (has_nan) atomicOr(&nanflag[P.b0 + blockIdx.z], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (NT + 31) / 32; ++w) best = kred[w] > best ? kred[w] : best;
+    atomicMax(&keys[P.b0 + blockIdx.z], best);
+  }
+}
+
+}  // namespace flow
+}  // namespace sofima
