@@ -147,6 +147,8 @@ struct Image {
   int ph, pw;           // patch extent
 };
 
+struct MeanPartial;
+
 struct Slot {
   int src;    // 0 = pre, 1 = post (flipped)
   int xform;  // 0: (v - mean) * valid, 1: valid indicator, 2: ((v - mean) * valid)^2
@@ -156,7 +158,9 @@ struct Problem {
   Image img[2];
   int dtype;               // SOFIMA_U8 | SOFIMA_F32
   const int32_t* starts[2];  // [B][2] (y, x), device
-  const float* means;      // [B][2]
+  const struct MeanPartial* parts;  // [B][2][kMeanGroups] partial patch sums
+  int has_mean;            // constant mean instead of the per-patch mean
+  float mean;
   int nslots;
   Slot slot[6];
   int PY;                  // max patch height (row capacity of T)
@@ -178,15 +182,21 @@ __device__ __forceinline__ float load_px(const void* data, int dtype, long long 
 }
 
 // Per-patch mean (flow_field.py:340-353): masked mean over the unmasked pixels.
-// One block per (pair, image); warps stride the rows, lanes stride the columns.
+// grid = (pair, image, row group): every block sums kMeanRows-th of the rows and
+// writes one (sum, count) partial; the consumers add the kMeanGroups partials in a
+// fixed order and divide (patch_mean()).  Sums are exact for uint8 images.
+constexpr int kMeanGroups = 8;
+
+struct MeanPartial {
+  double sum;
+  int count;
+  int pad;
+};
+
 __global__ void __launch_bounds__(kThreads)
-patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
+patch_mean_kernel(Problem P, MeanPartial* parts) {
   const int which = blockIdx.y;
   const long long b = P.b0 + blockIdx.x;
-  if (has_mean) {
-    if (threadIdx.x == 0) means_out[b * 2 + which] = mean;
-    return;
-  }
   const Image& I = P.img[which];
   const int y0 = clamp_start(P.starts[which][b * 2 + 0], I.ph, I.h);
   const int x0 = clamp_start(P.starts[which][b * 2 + 1], I.pw, I.w);
@@ -196,14 +206,17 @@ patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
     mx0 = clamp_start(P.starts[which][b * 2 + 1], I.pw, I.mw);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows_per = ceil_div(I.ph, kMeanGroups);
+  const int ya = blockIdx.z * rows_per, yb = min(I.ph, ya + rows_per);
   double sum = 0.0;
-  unsigned int isum = 0;  // <= 255 * rows * ceil(cols / 32) per thread: no overflow
+  unsigned int isum = 0;
   int cnt = 0;
-  for (int y = warp; y < I.ph; y += kThreads / 32) {
+  for (int y = ya + warp; y < yb; y += kThreads / 32) {
     const long long row = (long long)(y0 + y) * I.w + x0;
     const uint8_t* mrow = I.mask ? I.mask + (long long)(my0 + y) * I.mw + mx0 : nullptr;
     if (P.dtype == SOFIMA_U8) {
       const uint8_t* src = static_cast<const uint8_t*>(I.data) + row;
+#pragma unroll 4
       for (int x = lane; x < I.pw; x += 32) {
         const bool valid = mrow ? (mrow[x] == 0) : true;
         isum += valid ? (unsigned)src[x] : 0u;
@@ -211,6 +224,7 @@ patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
       }
     } else {
       const float* src = static_cast<const float*>(I.data) + row;
+#pragma unroll 4
       for (int x = lane; x < I.pw; x += 32) {
         const bool valid = mrow ? (mrow[x] == 0) : true;
         sum += valid ? (double)src[x] : 0.0;
@@ -231,9 +245,21 @@ patch_mean_kernel(Problem P, int has_mean, float mean, float* means_out) {
   if (threadIdx.x == 0) {
     double t = 0.0; int c = 0;
     for (int w = 0; w < kThreads / 32; ++w) { t += rs[w]; c += rc[w]; }
-    // fp32 sum / fp32 count, as jnp.mean / jnp.nanmean (0/0 -> NaN).
-    means_out[b * 2 + which] = __fdiv_rn((float)t, (float)c);
+    MeanPartial mp;
+    mp.sum = t; mp.count = c; mp.pad = 0;
+    parts[(b * 2 + which) * kMeanGroups + blockIdx.z] = mp;
   }
+}
+
+// fp32 sum / fp32 count, as jnp.mean / jnp.nanmean (0 / 0 -> NaN).
+__device__ __forceinline__ float patch_mean(const Problem& P, long long b, int which) {
+  if (P.has_mean) return P.mean;
+  const MeanPartial* mp = P.parts + (b * 2 + which) * kMeanGroups;
+  double t = 0.0;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < kMeanGroups; ++j) { t += mp[j].sum; c += mp[j].count; }
+  return __fdiv_rn((float)t, (float)c);
 }
 
 // ---------------------------------------------------------------------------------
@@ -261,7 +287,7 @@ rows_fwd_kernel(Problem P, FftPlan F, int R, float2* __restrict__ T) {
     my0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.mh);
     mx0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.mw);
   }
-  const float mean = P.means[b * 2 + sl.src];
+  const float mean = patch_mean(P, b, sl.src);
   const bool flip = sl.src == 1;  // curr[::-1, ::-1], flow_field.py:78-79
 
   auto sample = [&](int y, int x) -> float {
@@ -572,14 +598,25 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
   }
   const float thr = pp.thr_rel * v1;
   unsigned long long best = 0;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
-    const float v = im[i];
-    if (!(v > thr)) continue;
-    if ((bitmap[i >> 5] >> (i & 31)) & 1u) continue;  // erased for every row (:263-265)
+  auto consider = [&](int i, float v) {
+    if (!(v > thr)) return;
+    if ((bitmap[i >> 5] >> (i & 31)) & 1u) return;  // erased for every row (:263-265)
     const int y = i / pp.sx, x = i - y * pp.sx;
-    if (!is_peak(im, pp, y, x, v)) continue;
+    if (!is_peak(im, pp, y, x, v)) return;
     const unsigned long long k = peak_key(v, (unsigned)i);
     best = k > best ? k : best;
+  };
+  {
+    constexpr int U = 8;  // independent loads in flight per thread
+    int i = threadIdx.x;
+    for (; i + (U - 1) * kThreads < n; i += U * kThreads) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = __ldg(im + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) consider(i + u * kThreads, v[u]);
+    }
+    for (; i < n; i += kThreads) consider(i, __ldg(im + i));
   }
   best = block_max_key(best, sm);
 
@@ -761,15 +798,23 @@ template <int N2>
 static void launch_rows_fwd_fast(sofima_ctx* ctx, const Problem& P, const float2* tw, float2* T,
                                  int rp_max) {
   constexpr int TR = FastLines<N2>::n;
-  rows_fwd_fast<N2, TR><<<dim3(ceil_div(rp_max, TR), P.nslots, P.nb), TR * FastDims<N2>::G, 0,
-                         ctx->stream>>>(P, tw, T);
+  const dim3 grid(ceil_div(rp_max, TR), P.nslots, P.nb);
+  const bool half = 2 * P.img[0].pw <= FastDims<N2>::L && 2 * P.img[1].pw <= FastDims<N2>::L;
+  if (half)
+    rows_fwd_fast<N2, TR, true><<<grid, TR * FastDims<N2>::G, 0, ctx->stream>>>(P, tw, T);
+  else
+    rows_fwd_fast<N2, TR, false><<<grid, TR * FastDims<N2>::G, 0, ctx->stream>>>(P, tw, T);
 }
 template <int N2>
 static void launch_cols_fast(sofima_ctx* ctx, const Problem& P, const float2* tw, const float2* T,
                              float2* U) {
   constexpr int C = FastLines<N2>::n;
-  cols_fast<N2, C><<<dim3(ceil_div(P.nkx, C), P.nb), C * FastDims<N2>::G, 0, ctx->stream>>>(
-      P, tw, T, U);
+  const dim3 grid(ceil_div(P.nkx, C), P.nb);
+  const bool half = 2 * P.img[0].ph <= FastDims<N2>::L && 2 * P.img[1].ph <= FastDims<N2>::L;
+  if (half)
+    cols_fast<N2, C, true><<<grid, C * FastDims<N2>::G, 0, ctx->stream>>>(P, tw, T, U);
+  else
+    cols_fast<N2, C, false><<<grid, C * FastDims<N2>::G, 0, ctx->stream>>>(P, tw, T, U);
 }
 template <int N2>
 static void launch_rows_inv_fast(sofima_ctx* ctx, const Problem& P, const float2* tw,
@@ -886,7 +931,7 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   const size_t per_pair = sizeof(float2) * ((size_t)P.nslots * P.PY * P.nkx +
                                             (size_t)pr.nout * P.sy * P.nkx) +
                           (masked ? sizeof(float) * 6 * (size_t)P.sy * P.sx : 0);
-  long long nsub = (long long)((64ull << 20) / per_pair);
+  long long nsub = (long long)((96ull << 20) / per_pair);
   if (nsub < 1) nsub = 1;
   if (nsub > B) nsub = B;
   if (nsub > 65535) nsub = 65535;
@@ -895,8 +940,11 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
                     &Tbuf))) return rc;
   if ((rc = scratch(ctx, "flow.U", sizeof(float2) * (size_t)pr.nout * nsub * P.sy * P.nkx,
                     &Ubuf))) return rc;
-  if ((rc = scratch(ctx, "flow.means", sizeof(float) * 2 * B, &means))) return rc;
-  P.means = static_cast<const float*>(means);
+  if ((rc = scratch(ctx, "flow.means", sizeof(MeanPartial) * 2 * kMeanGroups * B, &means)))
+    return rc;
+  P.parts = static_cast<const MeanPartial*>(means);
+  P.has_mean = p->has_mean;
+  P.mean = p->mean;
   const size_t img_elems = (size_t)P.sy * P.sx;
   float *den_all = nullptr, *ov_all = nullptr;
   if (masked) {
@@ -916,10 +964,10 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
     const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
     P.b0 = b0;
     P.nb = nb;
-    {
+    if (!p->has_mean) {
       LaunchTimer timer(ctx, "flow_mean");
-      patch_mean_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, p->has_mean, p->mean,
-                                                                   (float*)means);
+      patch_mean_kernel<<<dim3(nb, 2, kMeanGroups), kThreads, 0, ctx->stream>>>(
+          P, (MeanPartial*)means);
       SOFIMA_CHECK_LAUNCH(ctx);
     }
     const int rp_max = (P.PY + 1) / 2;

@@ -40,23 +40,24 @@ __device__ __forceinline__ float2 swap_ri(float2 a) { return make_float2(a.y, a.
 // Stage 1: forward row FFTs (two real rows per complex transform).
 // grid = (row-pair groups, slot, pair), block = TR * N2 threads.
 // ---------------------------------------------------------------------------------
-template <int N2, int TR>
+template <int N2, int TR, bool HALF>
 __global__ void __launch_bounds__(TR * FastDims<N2>::G)
 rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) {
   using D = FastDims<N2>;
   constexpr int L = D::L;
+  constexpr int NT = TR * D::G;
+  constexpr int NKX = L / 2 + 1;
   __shared__ float2 ex[TR * D::EX];
-  __shared__ float2 xs[TR * L];
+  __shared__ float2 xs[TR * L];   // first the staged pixel rows (as float), then X
   __shared__ float2 tw_s[L];
+  float* px = reinterpret_cast<float*>(xs);  // [2 TR][L]
   const Slot sl = P.slot[blockIdx.y];
   const Image& I = P.img[sl.src];
   const long long b = P.b0 + blockIdx.z;
   const int rp0 = blockIdx.x * TR;
-  const int nrows = I.ph;
+  const int nrows = I.ph, pw = I.pw;
   if (2 * rp0 >= nrows) return;
-  constexpr int NT = TR * D::G;
   for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
-  __syncthreads();
 
   const int y0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.h);
   const int x0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.w);
@@ -65,29 +66,54 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
     my0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.mh);
     mx0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.mw);
   }
-  const float mean = P.means[b * 2 + sl.src];
+  const float mean = patch_mean(P, b, sl.src);
   const bool flip = sl.src == 1;  // curr[::-1, ::-1], flow_field.py:78-79
 
-  auto sample = [&](int y, int x) -> float {
-    if (y >= nrows) return 0.f;
-    const int yy = flip ? I.ph - 1 - y : y, xx = flip ? I.pw - 1 - x : x;
-    bool valid = true;
-    if (I.mask) valid = I.mask[(long long)(my0 + yy) * I.mw + mx0 + xx] == 0;
-    if (sl.xform == 1) return valid ? 1.f : 0.f;
-    float v = load_px(I.data, P.dtype, (long long)(y0 + yy) * I.w + x0 + xx) - mean;
-    v = valid ? v : 0.f;  // where(mask, 0, patch - mean), flow_field.py:73-76
-    return sl.xform == 2 ? v * v : v;
-  };
+  // Stage the 2 TR patch rows of this block: coalesced reads, one value per pixel
+  // = (pixel - mean) with masked pixels zeroed (flow_field.py:73-76), or the
+  // valid-mask indicator / the square for the Padfield terms.
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < 2 * TR; r += NT / 32) {
+      const int y = 2 * rp0 + r;
+      float* dst = px + r * L;
+      if (y >= nrows) {
+        for (int x = lane; x < pw; x += 32) dst[x] = 0.f;
+        continue;
+      }
+      const int yy = flip ? nrows - 1 - y : y;
+      const long long row = (long long)(y0 + yy) * I.w + x0;
+      const uint8_t* mrow = I.mask ? I.mask + (long long)(my0 + yy) * I.mw + mx0 : nullptr;
+      for (int x = lane; x < pw; x += 32) {
+        const int xx = flip ? pw - 1 - x : x;
+        const bool valid = mrow ? (mrow[xx] == 0) : true;
+        float v;
+        if (sl.xform == 1) {
+          v = valid ? 1.f : 0.f;
+        } else {
+          v = load_px(I.data, P.dtype, row + xx) - mean;
+          v = valid ? v : 0.f;
+          if (sl.xform == 2) v = v * v;
+        }
+        dst[x] = v;
+      }
+    }
+  }
+  __syncthreads();
 
   if (threadIdx.x < TR * N2) {  // pass 1: thread (f, n2)
     const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
-    const int y = 2 * (rp0 + f);
+    const float* r0 = px + (2 * f) * L;
+    const float* r1 = r0 + L;
     float2 a[kN1];
 #pragma unroll
     for (int n1 = 0; n1 < kN1; ++n1) {
       const int x = N2 * n1 + n2;
-      a[n1] = (x < I.pw && y < nrows) ? make_float2(sample(y, x), sample(y + 1, x))
-                                      : make_float2(0.f, 0.f);
+      if (HALF && n1 >= kN1 / 2) {
+        a[n1] = make_float2(0.f, 0.f);  // pw <= L / 2: compile-time zeros prune the DFT
+      } else {
+        a[n1] = (x < pw) ? make_float2(r0[x], r1[x]) : make_float2(0.f, 0.f);
+      }
     }
     Dft<kN1>::run(a);
 #pragma unroll
@@ -107,16 +133,21 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
   __syncthreads();
   // separate the two real rows: X_even = (Z[k] + conj Z[L-k]) / 2,
   //                             X_odd  = (Z[k] - conj Z[L-k]) / (2i)
-  float2* Tb = T + ((size_t)blockIdx.y * P.nb + blockIdx.z) * P.PY * P.nkx;
-  for (int i = threadIdx.x; i < TR * P.nkx; i += NT) {
-    const int f = i / P.nkx, k = i - f * P.nkx;
-    const int y = 2 * (rp0 + f);
-    if (y >= nrows) continue;
-    const float2 a = xs[f * L + k];
-    const float2 c = xs[f * L + (k == 0 ? 0 : L - k)];
-    Tb[(size_t)y * P.nkx + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
-    if (y + 1 < nrows)
-      Tb[(size_t)(y + 1) * P.nkx + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+  float2* Tb = T + ((size_t)blockIdx.y * P.nb + blockIdx.z) * P.PY * NKX;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int f = warp; f < TR; f += NT / 32) {
+      const int y = 2 * (rp0 + f);
+      if (y >= nrows) continue;
+      const bool two = y + 1 < nrows;
+      for (int k = lane; k < NKX; k += 32) {
+        const float2 a = xs[f * L + k];
+        const float2 c = xs[f * L + (k == 0 ? 0 : L - k)];
+        Tb[(size_t)y * NKX + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+        if (two)
+          Tb[(size_t)(y + 1) * NKX + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+      }
+    }
   }
 }
 
@@ -124,7 +155,7 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
 // Stage 2: forward column FFTs of both patches, product, inverse column FFT.
 // grid = (column groups, pair), block = C * N2 threads (c fastest).
 // ---------------------------------------------------------------------------------
-template <int N2, int C>
+template <int N2, int C, bool HALF>
 __global__ void __launch_bounds__(C * FastDims<N2>::G)
 cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T,
           float2* __restrict__ U) {
@@ -150,7 +181,11 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
 #pragma unroll
       for (int n1 = 0; n1 < kN1; ++n1) {
         const int y = N2 * n1 + r;
-        a[n1] = (col_ok && y < rows) ? Tb[(size_t)y * P.nkx] : make_float2(0.f, 0.f);
+        if (HALF && n1 >= kN1 / 2) {
+          a[n1] = make_float2(0.f, 0.f);  // rows <= L / 2: pruned by constant folding
+        } else {
+          a[n1] = (col_ok && y < rows) ? __ldg(Tb + (size_t)y * P.nkx) : make_float2(0.f, 0.f);
+        }
       }
       Dft<kN1>::run(a);
 #pragma unroll
@@ -217,26 +252,28 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
   const int rp0 = blockIdx.x * TR;
   if (2 * rp0 >= P.sy) return;
   for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
-  const float2* Ub = U + (size_t)blockIdx.z * P.sy * P.nkx;
+  constexpr int NKX = L / 2 + 1;
+  const float2* Ub = U + (size_t)blockIdx.z * P.sy * NKX;
   __syncthreads();
   if (threadIdx.x < TR * kN1) {  // thread (f, k1)
     const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
     const int y = 2 * (rp0 + f);
+    const bool row0 = y < P.sy, row1 = y + 1 < P.sy;
+    const float2* u0p = Ub + (size_t)min(y, P.sy - 1) * NKX;
+    const float2* u1p = Ub + (size_t)min(y + 1, P.sy - 1) * NKX;
     float2 bq[N2];
 #pragma unroll
     for (int k2 = 0; k2 < N2; ++k2) {
       const int k = k1 + kN1 * k2;
-      float2 z = make_float2(0.f, 0.f);
-      if (y < P.sy) {
-        const int kk = (k < P.nkx) ? k : L - k;
-        float2 u0 = Ub[(size_t)y * P.nkx + kk];
-        float2 u1 = (y + 1 < P.sy) ? Ub[(size_t)(y + 1) * P.nkx + kk] : make_float2(0.f, 0.f);
-        // c2r ignores the imaginary part of the DC and Nyquist bins.
-        if (kk == 0 || kk == L / 2) { u0.y = 0.f; u1.y = 0.f; }
-        if (k >= P.nkx) { u0.y = -u0.y; u1.y = -u1.y; }
-        z = make_float2(u0.x - u1.y, u0.y + u1.x);  // u0 + i u1
-      }
-      bq[k2] = swap_ri(z);
+      const bool mirror = k >= NKX;          // resolved per k2 except for one k2
+      const int kk = mirror ? L - k : k;
+      float2 u0 = __ldg(u0p + kk), u1 = __ldg(u1p + kk);
+      if (!row0) u0 = make_float2(0.f, 0.f);
+      if (!row1) u1 = make_float2(0.f, 0.f);
+      // c2r ignores the imaginary part of the DC and Nyquist bins.
+      if (kk == 0 || kk == L / 2) { u0.y = 0.f; u1.y = 0.f; }
+      if (mirror) { u0.y = -u0.y; u1.y = -u1.y; }
+      bq[k2] = make_float2(u0.y + u1.x, u0.x - u1.y);  // swap_ri(u0 + i u1)
     }
     Dft<N2>::run(bq);
 #pragma unroll
