@@ -487,11 +487,12 @@ padfield_normalise_kernel(float* xc, const float* ov, const float* den, long lon
 // Peaks (flow_field.py:205-275, :178-202).
 // ---------------------------------------------------------------------------------
 struct PeakParams {
-  int sy, sx;
-  int md;        // min_distance
+  int ndim;          // 2 or 3
+  int sz, sy, sx;    // correlation image extent (sz = 1 in 2-d)
+  int md;            // min_distance
   float thr_rel;
-  int ry, rx;    // peak_radius
-  int cy, cx;    // center_offset
+  int rz, ry, rx;    // peak_radius
+  int cz, cy, cx;    // center_offset
 };
 
 // order-preserving key: larger value first, then smaller flat index.
@@ -530,7 +531,7 @@ peak1_kernel(const float* __restrict__ img, PeakParams pp, unsigned long long* k
   __shared__ int nan_flag;
   if (threadIdx.x == 0) nan_flag = 0;
   __syncthreads();
-  const long long n = (long long)pp.sy * pp.sx;
+  const long long n = (long long)pp.sz * pp.sy * pp.sx;
   const float* im = img + blockIdx.x * n;
   unsigned long long best = 0;
   int has_nan = 0;
@@ -565,17 +566,21 @@ __global__ void peak1_decode_kernel(const unsigned long long* keys, const int* n
   atomicOr(&bitmap[p1[b] >> 5], 1u << (p1[b] & 31));
 }
 
-__device__ __forceinline__ bool is_peak(const float* im, const PeakParams& pp, int y, int x,
-                                        float v) {
+__device__ __forceinline__ bool is_peak(const float* im, const PeakParams& pp, int z, int y,
+                                        int x, float v) {
   // img == separable zero-padded max filter of width 2*md+1 (flow_field.py:237-254).
   float m = -INFINITY;
-  for (int dy = -pp.md; dy <= pp.md; ++dy) {
-    const int yy = y + dy;
-    for (int dx = -pp.md; dx <= pp.md; ++dx) {
-      const int xx = x + dx;
-      const float w = (yy < 0 || yy >= pp.sy || xx < 0 || xx >= pp.sx)
-                          ? 0.f : im[(long long)yy * pp.sx + xx];
-      m = fmaxf(m, w);
+  const int mz = pp.ndim == 3 ? pp.md : 0;
+  for (int dz = -mz; dz <= mz; ++dz) {
+    const int zz = z + dz;
+    for (int dy = -pp.md; dy <= pp.md; ++dy) {
+      const int yy = y + dy;
+      for (int dx = -pp.md; dx <= pp.md; ++dx) {
+        const int xx = x + dx;
+        const bool out = zz < 0 || zz >= pp.sz || yy < 0 || yy >= pp.sy || xx < 0 || xx >= pp.sx;
+        const float w = out ? 0.f : im[((long long)zz * pp.sy + yy) * pp.sx + xx];
+        m = fmaxf(m, w);
+      }
     }
   }
   return v == m;
@@ -587,7 +592,7 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
              const unsigned* __restrict__ bitmap, int ndim_out, float* out) {
   __shared__ unsigned long long sm[kThreads / 32];
   __shared__ float smin[kThreads / 32];
-  const long long n = (long long)pp.sy * pp.sx;
+  const long long n = (long long)pp.sz * pp.sy * pp.sx;
   const float* im = img + blockIdx.x * n;
   float* o = out + (long long)blockIdx.x * ndim_out;
   const float v1 = v1a[blockIdx.x];
@@ -601,8 +606,9 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
   auto consider = [&](int i, float v) {
     if (!(v > thr)) return;
     if ((bitmap[i >> 5] >> (i & 31)) & 1u) return;  // erased for every row (:263-265)
-    const int y = i / pp.sx, x = i - y * pp.sx;
-    if (!is_peak(im, pp, y, x, v)) return;
+    const int x = i % pp.sx, r = i / pp.sx;
+    const int y = r % pp.sy, z = r / pp.sy;
+    if (!is_peak(im, pp, z, y, x, v)) return;
     const unsigned long long k = peak_key(v, (unsigned)i);
     best = k > best ? k : best;
   };
@@ -621,20 +627,19 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
   best = block_max_key(best, sm);
 
   // Sharpness: peak / min over a (2r+1) window with clamped start (:190-192).
-  const int py = p1 / pp.sx, px = p1 - py * pp.sx;
-  const int wy = 2 * pp.ry + 1, wx = 2 * pp.rx + 1;
+  const int px = p1 % pp.sx, pr = p1 / pp.sx;
+  const int py = pr % pp.sy, pz = pr / pp.sy;
+  const int wz = pp.ndim == 3 ? 2 * pp.rz + 1 : 1, wy = 2 * pp.ry + 1, wx = 2 * pp.rx + 1;
+  const int z0 = pp.ndim == 3 ? clamp_start(pz - pp.rz, wz, pp.sz) : 0;
   const int y0 = clamp_start(py - pp.ry, wy, pp.sy), x0 = clamp_start(px - pp.rx, wx, pp.sx);
   float mn = INFINITY;
-  bool nan_seen = false;
-  for (int i = threadIdx.x; i < wy * wx; i += kThreads) {
-    const int yy = y0 + i / wx, xx = x0 + i % wx;
-    const float v = im[(long long)yy * pp.sx + xx];
-    if (v != v) nan_seen = true;
-    mn = fminf(mn, v);
+  for (int i = threadIdx.x; i < wz * wy * wx; i += kThreads) {
+    const int xx = x0 + i % wx, rr = i / wx;
+    const int yy = y0 + rr % wy, zz = z0 + rr / wy;
+    mn = fminf(mn, im[((long long)zz * pp.sy + yy) * pp.sx + xx]);
   }
 #pragma unroll
   for (int of = 16; of > 0; of >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, of));
-  (void)nan_seen;
   if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = mn;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -647,12 +652,14 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
       // argmax of an all -inf row is index 0; the value is read from the
       // un-erased array (flow_field.py:266-268).
       const float v0 = im[0];
-      v2 = (v0 > thr && is_peak(im, pp, 0, 0, v0)) ? v0 : -INFINITY;
+      v2 = (v0 > thr && is_peak(im, pp, 0, 0, 0, v0)) ? v0 : -INFINITY;
     }
-    o[0] = (float)px - (float)pp.cx;
-    o[1] = (float)py - (float)pp.cy;
-    o[2] = v1 / mn;
-    o[3] = (v2 == -INFINITY || v2 == INFINITY) ? 0.0f : v1 / v2;
+    int c = 0;
+    o[c++] = (float)px - (float)pp.cx;
+    o[c++] = (float)py - (float)pp.cy;
+    if (pp.ndim == 3) o[c++] = (float)pz - (float)pp.cz;
+    o[c++] = v1 / mn;
+    o[c++] = (v2 == -INFINITY || v2 == INFINITY) ? 0.0f : v1 / v2;
   }
 }
 
@@ -726,8 +733,10 @@ static int make_plan(sofima_ctx* ctx, int L, FftPlan* P) {
 static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const PeakParams& pp,
                      float* out_peaks, bool keys_ready) {
   if (B == 0) return SOFIMA_OK;
-  const long long n = (long long)pp.sy * pp.sx;
-  if (2 * pp.ry + 1 > pp.sy || 2 * pp.rx + 1 > pp.sx)
+  const long long n = (long long)pp.sz * pp.sy * pp.sx;
+  if (n > INT32_MAX) return fail(ctx, SOFIMA_EINVAL, "correlation image too large");
+  if (2 * pp.ry + 1 > pp.sy || 2 * pp.rx + 1 > pp.sx ||
+      (pp.ndim == 3 && 2 * pp.rz + 1 > pp.sz))
     return fail(ctx, SOFIMA_EINVAL, "peak_radius window larger than the correlation image");
   void *v1 = nullptr, *p1 = nullptr, *bm = nullptr, *keys = nullptr, *nanf = nullptr;
   int rc;
@@ -753,7 +762,7 @@ static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const Pe
     LaunchTimer timer(ctx, "flow_peak2");
     peak2_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (const float*)v1,
                                                             (const int*)p1, (const unsigned*)bm,
-                                                            4, out_peaks);
+                                                            pp.ndim + 2, out_peaks);
     SOFIMA_CHECK_LAUNCH(ctx);
   }
   return SOFIMA_OK;
@@ -761,12 +770,10 @@ static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const Pe
 
 static int check_params(sofima_ctx* ctx, const sofima_xcorr_params* p) {
   if (!p) return fail(ctx, SOFIMA_EINVAL, "params is NULL");
-  if (p->ndim == 3)
-    return fail(ctx, SOFIMA_EUNSUPPORTED, "3-d patch correlation is not built yet");
-  if (p->ndim != 2) return fail(ctx, SOFIMA_EINVAL, "ndim must be 2 or 3");
+  if (p->ndim != 2 && p->ndim != 3) return fail(ctx, SOFIMA_EINVAL, "ndim must be 2 or 3");
   if (p->img_dtype != SOFIMA_U8 && p->img_dtype != SOFIMA_F32)
     return fail(ctx, SOFIMA_EINVAL, "img_dtype must be SOFIMA_U8 or SOFIMA_F32");
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < p->ndim; ++d) {
     if (p->pre_patch[d] < 1 || p->post_patch[d] < 1)
       return fail(ctx, SOFIMA_EINVAL, "patch sizes must be positive");
     if (p->pre_patch[d] > p->pre_shape[d] || p->post_patch[d] > p->post_shape[d])
@@ -1064,6 +1071,138 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
 }  // namespace flow
 }  // namespace sofima
 
+#include "flow3d.cuh"
+
+namespace sofima {
+namespace flow {
+
+// 3-d correlation images of one batch into `images` [B][sz][sy][sx] (unmasked).
+static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                      const void* post_img, const uint8_t* pre_mask, const uint8_t* post_mask,
+                      const int32_t* pre_starts, const int32_t* post_starts, long long B,
+                      float* images) {
+  if (pre_mask || post_mask)
+    return fail(ctx, SOFIMA_EUNSUPPORTED, "masked 3-d correlation is not built yet");
+  Problem3 P;
+  memset(&P, 0, sizeof(P));
+  P.dtype = p->img_dtype;
+  const void* datas[2] = {pre_img, post_img};
+  const int64_t* shapes[2] = {p->pre_shape, p->post_shape};
+  const int32_t* patches[2] = {p->pre_patch, p->post_patch};
+  for (int i = 0; i < 2; ++i) {
+    P.img[i].data = datas[i];
+    P.img[i].d = (int)shapes[i][0]; P.img[i].h = (int)shapes[i][1]; P.img[i].w = (int)shapes[i][2];
+    P.img[i].pd = patches[i][0]; P.img[i].ph = patches[i][1]; P.img[i].pw = patches[i][2];
+  }
+  P.starts[0] = pre_starts;
+  P.starts[1] = post_starts;
+  P.has_mean = p->has_mean;
+  P.mean = p->mean;
+  P.sz = p->pre_patch[0] + p->post_patch[0] - 1;
+  P.sy = p->pre_patch[1] + p->post_patch[1] - 1;
+  P.sx = p->pre_patch[2] + p->post_patch[2] - 1;
+  P.Lz = next_fast_len(P.sz); P.Ly = next_fast_len(P.sy); P.Lx = next_fast_len(P.sx);
+  FftPlan Fz, Fy, Fx;
+  int rc;
+  if ((rc = make_plan(ctx, P.Lz, &Fz))) return rc;
+  if ((rc = make_plan(ctx, P.Ly, &Fy))) return rc;
+  if ((rc = make_plan(ctx, P.Lx, &Fx))) return rc;
+  const long long vol = (long long)P.Lz * P.Ly * P.Lx;
+  long long nsub = (long long)((512ull << 20) / (2 * vol * sizeof(float2)));
+  if (nsub < 1) nsub = 1;
+  if (nsub > B) nsub = B;
+  void *Z = nullptr, *means = nullptr;
+  if ((rc = scratch(ctx, "flow3.Z", sizeof(float2) * 2 * nsub * vol, &Z))) return rc;
+  if ((rc = scratch(ctx, "flow3.means", sizeof(float) * 2 * B, &means))) return rc;
+  const size_t smem_cap = 200 * 1024;
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(axis_fft_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(axis_fft_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+  auto lines_per_block = [&](int L) {
+    int C = 16;
+    while (C > 1 && (size_t)(2 * C + 1) * L * sizeof(float2) > 96 * 1024) C /= 2;
+    return C;
+  };
+  const float scale = (float)(1.0 / ((double)P.Lx * P.Ly * P.Lz));
+  for (long long b0 = 0; b0 < B; b0 += nsub) {
+    const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
+    P.b0 = b0;
+    P.nb = nb;
+    float2* Zp = static_cast<float2*>(Z);
+    {
+      LaunchTimer timer(ctx, "flow3_pack");
+      patch_mean3_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, (float*)means);
+      SOFIMA_CHECK_LAUNCH(ctx);
+      pack3_kernel<<<dim3(ctx->num_sms * 2, 2, nb), kThreads, 0, ctx->stream>>>(
+          P, (const float*)means, Zp);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    // transforms over x, y, z of all 2 * nb volumes (forward), then of the nb products.
+    auto transform = [&](bool inverse, long long nvol) -> int {
+      struct Axis { const FftPlan* F; long long nlines, inner, istride, ostride, es; };
+      const long long plane = (long long)P.Ly * P.Lx;
+      const Axis axes[3] = {
+          {&Fx, nvol * P.Lz * P.Ly, 1, 0, P.Lx, 1},                       // x: contiguous lines
+          {&Fy, nvol * P.Lz * P.Lx, P.Lx, 1, plane, P.Lx},                // y: lines (z, x)
+          {&Fz, nvol * plane, plane, 1, vol, plane},                      // z: lines (y, x)
+      };
+      for (int a = 0; a < 3; ++a) {
+        const Axis& A = axes[inverse ? 2 - a : a];
+        const int C = lines_per_block(A.F->L);
+        const size_t smem = (size_t)(2 * C + 1) * A.F->L * sizeof(float2);
+        const unsigned grid = (unsigned)ceil_div<long long>(A.nlines, C);
+        LaunchTimer timer(ctx, "flow3_fft");
+        if (inverse)
+          axis_fft_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(
+              Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+        else
+          axis_fft_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(
+              Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+        SOFIMA_CHECK_LAUNCH(ctx);
+      }
+      return SOFIMA_OK;
+    };
+    if ((rc = transform(false, 2ll * nb))) return rc;
+    {
+      LaunchTimer timer(ctx, "flow3_mul");
+      multiply3_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(Zp, Zp + (long long)nb * vol,
+                                                                        (long long)nb * vol);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    if ((rc = transform(true, nb))) return rc;
+    {
+      LaunchTimer timer(ctx, "flow3_crop");
+      crop3_kernel<<<dim3(ctx->num_sms * 2, nb), kThreads, 0, ctx->stream>>>(P, Zp, images, scale);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+  }
+  return SOFIMA_OK;
+}
+
+static void peak_params(const sofima_xcorr_params* p, PeakParams* pp) {
+  memset(pp, 0, sizeof(*pp));
+  const int nd = p->ndim, o = 3 - nd;  // o: offset of the y axis slot in (z, y, x)
+  int s[3] = {1, 1, 1}, r[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+  for (int d = 0; d < nd; ++d) {
+    s[o + d] = p->pre_patch[d] + p->post_patch[d] - 1;
+    r[o + d] = p->peak_radius[d];
+    // center_offset = (pre + post) // 2 - 1, flow_field.py:357-360
+    c[o + d] = (p->pre_patch[d] + p->post_patch[d]) / 2 - 1;
+  }
+  pp->ndim = nd;
+  pp->sz = s[0]; pp->sy = s[1]; pp->sx = s[2];
+  pp->rz = r[0]; pp->ry = r[1]; pp->rx = r[2];
+  pp->cz = c[0]; pp->cy = c[1]; pp->cx = c[2];
+  pp->md = p->min_distance;
+  pp->thr_rel = p->threshold_rel;
+}
+
+}  // namespace flow
+}  // namespace sofima
+
 extern "C" {
 
 int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
@@ -1079,6 +1218,9 @@ int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p, const voi
   if (!pre_img || !post_img || !pre_starts || !post_starts || !out_xcorr)
     return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
   DeviceGuard guard(ctx->device);
+  if (p->ndim == 3)
+    return flow::run_xcorr3(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
+                            post_starts, batch, out_xcorr);
   return flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
                          post_starts, batch, out_xcorr, nullptr);
 }
@@ -1096,25 +1238,20 @@ int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void
   if (!pre_img || !post_img || !pre_starts || !post_starts || !out_peaks)
     return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
   DeviceGuard guard(ctx->device);
-  const int sy = p->pre_patch[0] + p->post_patch[0] - 1;
-  const int sx = p->pre_patch[1] + p->post_patch[1] - 1;
+  flow::PeakParams pp;
+  flow::peak_params(p, &pp);
+  const size_t img_elems = (size_t)pp.sz * pp.sy * pp.sx;
   void* images = nullptr;
-  if ((rc = scratch(ctx, "flow.images", sizeof(float) * (size_t)batch * sy * sx, &images)))
+  if ((rc = scratch(ctx, "flow.images", sizeof(float) * (size_t)batch * img_elems, &images)))
     return rc;
   bool keys_ready = false;
-  rc = flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts, post_starts,
-                       batch, static_cast<float*>(images), &keys_ready);
+  if (p->ndim == 3)
+    rc = flow::run_xcorr3(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
+                          post_starts, batch, static_cast<float*>(images));
+  else
+    rc = flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
+                         post_starts, batch, static_cast<float*>(images), &keys_ready);
   if (rc) return rc;
-  flow::PeakParams pp;
-  pp.sy = sy;
-  pp.sx = sx;
-  pp.md = p->min_distance;
-  pp.thr_rel = p->threshold_rel;
-  pp.ry = p->peak_radius[0];
-  pp.rx = p->peak_radius[1];
-  // center_offset = (pre + post) // 2 - 1, flow_field.py:357-360
-  pp.cy = (p->pre_patch[0] + p->post_patch[0]) / 2 - 1;
-  pp.cx = (p->pre_patch[1] + p->post_patch[1]) / 2 - 1;
   return flow::run_peaks(ctx, static_cast<const float*>(images), batch, pp, out_peaks,
                          keys_ready);
 }
@@ -1124,24 +1261,29 @@ int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img, const int6
                          float threshold_rel, const int32_t* peak_radius, float* out_peaks) {
   using namespace sofima;
   if (!ctx) return fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
-  if (ndim == 3) return fail(ctx, SOFIMA_EUNSUPPORTED, "3-d peak search is not built yet");
-  if (ndim != 2) return fail(ctx, SOFIMA_EINVAL, "ndim must be 2 or 3");
+  if (ndim != 2 && ndim != 3) return fail(ctx, SOFIMA_EINVAL, "ndim must be 2 or 3");
   if (batch < 0) return fail(ctx, SOFIMA_EINVAL, "batch < 0");
   if (batch == 0) return SOFIMA_OK;
   if (!img || !img_shape || !center_offset || !peak_radius || !out_peaks)
     return fail(ctx, SOFIMA_EINVAL, "NULL array argument");
-  if (img_shape[0] * img_shape[1] > INT32_MAX || min_distance < 0)
-    return fail(ctx, SOFIMA_EINVAL, "image too large");
+  if (min_distance < 0) return fail(ctx, SOFIMA_EINVAL, "min_distance < 0");
   DeviceGuard guard(ctx->device);
   flow::PeakParams pp;
-  pp.sy = (int)img_shape[0];
-  pp.sx = (int)img_shape[1];
+  memset(&pp, 0, sizeof(pp));
+  const int o = 3 - ndim;
+  int sh[3] = {1, 1, 1}, r[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+  for (int d = 0; d < ndim; ++d) {
+    if (img_shape[d] > INT32_MAX) return fail(ctx, SOFIMA_EINVAL, "image too large");
+    sh[o + d] = (int)img_shape[d];
+    r[o + d] = peak_radius[d];
+    c[o + d] = center_offset[d];
+  }
+  pp.ndim = ndim;
+  pp.sz = sh[0]; pp.sy = sh[1]; pp.sx = sh[2];
+  pp.rz = r[0]; pp.ry = r[1]; pp.rx = r[2];
+  pp.cz = c[0]; pp.cy = c[1]; pp.cx = c[2];
   pp.md = min_distance;
   pp.thr_rel = threshold_rel;
-  pp.ry = peak_radius[0];
-  pp.rx = peak_radius[1];
-  pp.cy = center_offset[0];
-  pp.cx = center_offset[1];
   return flow::run_peaks(ctx, img, batch, pp, out_peaks, false);
 }
 

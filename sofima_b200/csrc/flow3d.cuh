@@ -1,0 +1,162 @@
+// 3-d patch correlation (reference flow_field.py:36-89 with dim = 3, unmasked).
+//
+// Correctness-first: every patch is packed into a zero-padded complex volume
+// [Lz][Ly][Lx], transformed along x, y, z with the generic shared-memory Stockham
+// FFT (strided lines), multiplied, transformed back and cropped.  The peak kernels
+// of flow.cu are dimension-generic.  (The 2-d kernels are the tuned path; 3-d
+// volumes appear in BASELINE config 5 only.)
+#pragma once
+
+namespace sofima {
+namespace flow {
+
+struct Vol3 {
+  const void* data;
+  int d, h, w;     // image extent (z, y, x)
+  int pd, ph, pw;  // patch extent
+};
+
+struct Problem3 {
+  Vol3 img[2];
+  int dtype;
+  const int32_t* starts[2];  // [B][3] (z, y, x)
+  int has_mean;
+  float mean;
+  int Lz, Ly, Lx;
+  int sz, sy, sx;
+  long long b0;
+  int nb;
+};
+
+// mean of one 3-d patch; grid = (pair, image), deterministic fp64 accumulation.
+__global__ void __launch_bounds__(kThreads)
+patch_mean3_kernel(Problem3 P, float* means) {
+  const int which = blockIdx.y;
+  const long long b = P.b0 + blockIdx.x;
+  if (P.has_mean) {
+    if (threadIdx.x == 0) means[b * 2 + which] = P.mean;
+    return;
+  }
+  const Vol3& I = P.img[which];
+  const int z0 = clamp_start(P.starts[which][b * 3 + 0], I.pd, I.d);
+  const int y0 = clamp_start(P.starts[which][b * 3 + 1], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[which][b * 3 + 2], I.pw, I.w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double sum = 0.0;
+  for (int r = warp; r < I.pd * I.ph; r += kThreads / 32) {
+    const int z = r / I.ph, y = r - z * I.ph;
+    const long long row = ((long long)(z0 + z) * I.h + (y0 + y)) * I.w + x0;
+    for (int x = lane; x < I.pw; x += 32) sum += (double)load_px(I.data, P.dtype, row + x);
+  }
+  __shared__ double rs[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) rs[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += rs[w];
+    means[b * 2 + which] = __fdiv_rn((float)t, (float)(I.pd * I.ph * I.pw));
+  }
+}
+
+// Z[slot][pair] = zero-padded (patch - mean), the post patch flipped on all axes.
+__global__ void __launch_bounds__(kThreads)
+pack3_kernel(Problem3 P, const float* __restrict__ means, float2* __restrict__ Z) {
+  const int which = blockIdx.y;
+  const long long b = P.b0 + blockIdx.z;
+  const Vol3& I = P.img[which];
+  const int z0 = clamp_start(P.starts[which][b * 3 + 0], I.pd, I.d);
+  const int y0 = clamp_start(P.starts[which][b * 3 + 1], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[which][b * 3 + 2], I.pw, I.w);
+  const float mean = means[b * 2 + which];
+  const bool flip = which == 1;
+  const long long vol = (long long)P.Lz * P.Ly * P.Lx;
+  float2* out = Z + ((long long)which * P.nb + blockIdx.z) * vol;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < vol;
+       i += (long long)gridDim.x * kThreads) {
+    const int x = (int)(i % P.Lx);
+    const long long r = i / P.Lx;
+    const int y = (int)(r % P.Ly), z = (int)(r / P.Ly);
+    float v = 0.f;
+    if (z < I.pd && y < I.ph && x < I.pw) {
+      const int zz = flip ? I.pd - 1 - z : z, yy = flip ? I.ph - 1 - y : y,
+                xx = flip ? I.pw - 1 - x : x;
+      v = load_px(I.data, P.dtype, ((long long)(z0 + zz) * I.h + (y0 + yy)) * I.w + x0 + xx) -
+          mean;
+    }
+    out[i] = make_float2(v, 0.f);
+  }
+}
+
+// In-place complex FFT of `nlines` strided lines of length F.L:
+//   line l starts at (l / inner) * outer_stride + (l % inner) * inner_stride,
+//   consecutive elements are `es` apart.  C lines per block.
+template <bool INV>
+__global__ void __launch_bounds__(kThreads)
+axis_fft_kernel(float2* __restrict__ data, long long nlines, long long inner,
+                long long inner_stride, long long outer_stride, long long es, FftPlan F,
+                int C) {
+  extern __shared__ float2 smem[];
+  const int L = F.L;
+  float2* w0 = smem;
+  float2* w1 = w0 + (size_t)C * L;
+  float2* tw_s = w1 + (size_t)C * L;
+  load_twiddles(tw_s, F);
+  const long long l0 = (long long)blockIdx.x * C;
+  const int nc = (int)min((long long)C, nlines - l0);
+  auto line_base = [&](long long l) {
+    return (l / inner) * outer_stride + (l % inner) * inner_stride;
+  };
+  if (es == 1) {
+    for (int i = threadIdx.x; i < C * L; i += kThreads) {
+      const int c = i / L, k = i - c * L;
+      w0[i] = c < nc ? data[line_base(l0 + c) + k] : make_float2(0.f, 0.f);
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * L; i += kThreads) {
+      const int k = i / C, c = i - k * C;  // c fastest: neighbouring lines are adjacent
+      w0[c * L + k] = c < nc ? data[line_base(l0 + c) + (long long)k * es]
+                             : make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  const float2* res = block_fft<INV>(w0, w1, C, F, tw_s);
+  if (es == 1) {
+    for (int i = threadIdx.x; i < C * L; i += kThreads) {
+      const int c = i / L, k = i - c * L;
+      if (c < nc) data[line_base(l0 + c) + k] = res[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * L; i += kThreads) {
+      const int k = i / C, c = i - k * C;
+      if (c < nc) data[line_base(l0 + c) + (long long)k * es] = res[c * L + k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+multiply3_kernel(float2* __restrict__ a, const float2* __restrict__ b, long long n) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads)
+    a[i] = cmul(a[i], b[i]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+crop3_kernel(Problem3 P, const float2* __restrict__ Z, float* __restrict__ images,
+             float scale) {
+  const long long vol = (long long)P.Lz * P.Ly * P.Lx;
+  const long long n = (long long)P.sz * P.sy * P.sx;
+  const float2* in = Z + (long long)blockIdx.y * vol;
+  float* out = images + (P.b0 + blockIdx.y) * n;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads) {
+    const int x = (int)(i % P.sx);
+    const long long r = i / P.sx;
+    const int y = (int)(r % P.sy), z = (int)(r / P.sy);
+    out[i] = in[((long long)z * P.Ly + y) * P.Lx + x].x * scale;
+  }
+}
+
+}  // namespace flow
+}  // namespace sofima

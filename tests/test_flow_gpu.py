@@ -90,11 +90,41 @@ def test_kat_post_targeting(ff):
   np.testing.assert_array_equal(-50 * np.ones((2, 2)), field[1])
 
 
-def test_kat_3d_not_built(ff):
+def test_kat_3d(ff, flow_golden):  # flow_field_test.py:58-72
   pre = np.zeros((50, 100, 100), np.uint8)
-  with pytest.raises(NotImplementedError):  # fails loudly, no CPU fallback
+  post = np.zeros((50, 100, 100), np.uint8)
+  pre[25, 50, 50] = 255
+  post[22, 45, 54] = 255
+  flow = ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
+      pre, post, patch_size=(40, 80, 80), step=10, batch_size=1)
+  np.testing.assert_array_equal([5, 2, 3, 3], flow.shape)
+  np.testing.assert_array_equal(np.full([2, 3, 3], -4), flow[0])
+  np.testing.assert_array_equal(np.full([2, 3, 3], 5), flow[1])
+  np.testing.assert_array_equal(np.full([2, 3, 3], 3), flow[2])
+  want = flow_golden['kat_3d_flow']
+  np.testing.assert_array_equal(flow[:3], want[:3])
+  np.testing.assert_array_equal(flow[4], want[4])
+
+
+def test_3d_textures_match_oracle(ff):
+  rng = np.random.default_rng(4)
+  base = ndi.gaussian_filter(rng.standard_normal((40, 90, 100)), 1.2)
+  base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+  pre = np.ascontiguousarray(base[4:34, 8:78, 10:90])
+  post = np.ascontiguousarray(base[5:35, 6:76, 13:93])
+  kw = dict(patch_size=(16, 32, 40), step=(7, 19, 20), batch_size=5)
+  got = ff.JAXMaskedXCorrWithStatsCalculator(peak_radius=(2, 3, 4)).flow_field(pre, post, **kw)
+  want = fo.MaskedXCorrWithStatsCalculator(peak_radius=(2, 3, 4)).flow_field(pre, post, **kw)
+  assert got.shape == want.shape and got.shape[0] == 5
+  _check_flow(got, want)
+  # _batched_peaks in 3-d on oracle correlation volumes
+  center, xc = fo.batched_xcorr(pre, post, None, None, (16, 32, 40),
+                                np.array([[0, 0, 0], [7, 19, 20], [14, 38, 40]]), None)
+  np.testing.assert_allclose(ff._batched_peaks(xc, center, 2, 0.5, (2, 3, 4)),
+                             fo.batched_peaks(xc, center, 2, 0.5, (2, 3, 4)), rtol=1e-5)
+  with pytest.raises(NotImplementedError):  # masked 3-d: fails loudly
     ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
-        pre, pre, patch_size=(40, 80, 80), step=10, batch_size=1)
+        pre, post, pre_mask=np.zeros(pre.shape, bool), **kw)
 
 
 # ---- golden vectors from the reference source -------------------------------------
