@@ -132,6 +132,31 @@ int sofima_mesh_chunk_async(sofima_ctx* ctx, int force_kind, float* x, float* v,
                             float alpha, float cap,
                             sofima_mesh_state* results_pinned);
 
+/* ---- One mesh sharded by rows over the GPUs of a node (BASELINE config 3) ----
+ * No counterpart in the reference (a section is always solved on one device,
+ * processor/mesh.py:462); numerically it is mesh.velocity_verlet on the whole mesh.
+ * Every rank (one process per GPU) owns a slab of rows [2][nb][ny_local][nx];
+ * slabs of ranks that have a lower neighbour must be a multiple of 32 rows.  The
+ * step kernels read the neighbours' boundary rows and exchange the FIRE partial
+ * sums through peer-mapped memory (CUDA IPC over NVLink), flag-synchronised on the
+ * device: no host round trip and no collective call inside a chunk.
+ *   create -> export (128-byte blob per rank) -> all-gather the blobs on the host
+ *   -> connect -> set_state -> [host barrier] chunk ... -> get_state -> destroy
+ * `chunk` returns the rank-LOCAL e_kin / v_max; the caller all-reduces them. */
+typedef struct sofima_mesh_shard sofima_mesh_shard;
+#define SOFIMA_SHARD_BLOB_BYTES 128
+int sofima_shard_create(sofima_ctx* ctx, int rank, int nranks,
+                        const sofima_mesh_shape* local_shape, sofima_mesh_shard** out);
+int sofima_shard_export(sofima_mesh_shard* shard, void* blob128);
+int sofima_shard_connect(sofima_mesh_shard* shard, const void* blobs /* nranks * 128 B */);
+int sofima_shard_set_state(sofima_mesh_shard* shard, const float* x, const float* v_or_null,
+                           const float* prev_or_null);
+int sofima_shard_chunk(sofima_mesh_shard* shard, const sofima_integration_config* cfg,
+                       float dt, float alpha, float cap, int64_t global_nodes,
+                       sofima_mesh_state* result);
+int sofima_shard_get_state(sofima_mesh_shard* shard, float* x, float* v, float* a);
+int sofima_shard_destroy(sofima_mesh_shard* shard);
+
 /* ------------------------------------------------------------------------- *
  *  Patch flow  (reference: flow_field.py)
  * ------------------------------------------------------------------------- */

@@ -159,6 +159,16 @@ _PROTOS = {
         _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.POINTER(MeshShape),
         ctypes.POINTER(IntegrationConfigPod), ctypes.c_float, ctypes.c_float,
         ctypes.c_float, _vp]),
+    'sofima_shard_create': (ctypes.c_int, [
+        _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(MeshShape), ctypes.POINTER(_vp)]),
+    'sofima_shard_export': (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    'sofima_shard_connect': (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    'sofima_shard_set_state': (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    'sofima_shard_chunk': (ctypes.c_int, [
+        _vp, ctypes.POINTER(IntegrationConfigPod), ctypes.c_float, ctypes.c_float,
+        ctypes.c_float, ctypes.c_int64, ctypes.POINTER(MeshState)]),
+    'sofima_shard_get_state': (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    'sofima_shard_destroy': (ctypes.c_int, [_vp]),
     'sofima_xcorr_peaks': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_int64, _vp]),

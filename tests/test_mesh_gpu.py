@@ -236,3 +236,27 @@ def test_full_size_properties(mesh):
   # (3) determinism: two runs are bitwise identical.
   out1b, _, _ = mesh.relax_mesh(torch.zeros_like(p1), p1, cfg)
   assert torch.equal(out1, out1b)
+
+
+def test_sharded_single_rank_equals_relax_mesh(mesh):
+  """The sharded step kernel (device-side flags, mailbox FIRE state) with one rank
+  must reproduce relax_mesh bit for bit."""
+  import scipy.ndimage as ndi
+  from sofima_b200 import mesh_sharded
+  rng = np.random.default_rng(9)
+  shape = (2, 2, 70, 45)
+  prev = (ndi.gaussian_filter(rng.standard_normal(shape), (0, 0, 3, 3)) * 20).astype(np.float32)
+  prev[rng.random(shape) < 0.01] = np.nan
+  x0 = np.zeros(shape, np.float32)
+  for kw in (dict(fire=True, prefer_orig_order=True),
+             dict(fire=True, remove_drift=True, dt_max=100.0, k0=0.02),
+             dict(fire=False, gamma=0.5, dt=0.05)):
+    base = dict(dt=0.001, gamma=0.0, k0=0.1, k=0.1, stride=(40.0, 40.0), num_iters=60,
+                max_iters=180, stop_v_max=0.0, dt_max=1000.0)
+    base.update(kw)
+    cfg = mesh.IntegrationConfig(**base)
+    want, ek_w, t_w = mesh.relax_mesh(x0, prev, cfg)
+    got, ek_g, t_g = mesh_sharded.relax_mesh_sharded(x0, prev, cfg)
+    assert t_g == t_w
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_allclose(ek_g, ek_w, rtol=1e-12)
