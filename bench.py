@@ -402,12 +402,22 @@ def run_ours(args):
 
   # ---------------- mesh ----------------
   if args.path in ('both', 'mesh'):
+    from sofima_b200 import mesh_sharded
     iters = args.mesh_iters
     cfg = mesh_config(mesh, iters)
-    prev = synth_mesh(MESH_N, 7 + rank, dev)
+    nodes = MESH_N * MESH_N
+    # N > 1: ONE 2048^2 mesh, rows sharded over the ranks (strong scaling); every
+    # rank synthesises the same field and keeps its slab.
+    prev_full = synth_mesh(MESH_N, 7, dev)
+    y0, y1 = mesh_sharded.partition_rows(MESH_N, world)[rank]
+    prev = prev_full[:, :, y0:y1].contiguous()
+    del prev_full
     x0 = torch.zeros_like(prev)
-    chunk = mesh._Chunk(x0, None, prev, cfg, 0)
     state = {'dt': cfg.dt, 'alpha': cfg.alpha, 'cap': cfg.start_cap}
+    if world == 1:
+      chunk = mesh._Chunk(x0, None, prev, cfg, 0)
+    else:
+      chunk = mesh_sharded.ShardedMesh(x0, prev, cfg)
 
     def mesh_step(i):
       dt, alpha, _, cap, _, _ = chunk.run(state['dt'], state['alpha'], state['cap'])
@@ -418,24 +428,29 @@ def run_ours(args):
     with ClockSampler(local) as cs:
       ms, launches = timed(mesh_step, K)
     clocks['mesh'] = cs.summary()
-    nodes = MESH_N * MESH_N
-    mesh_value = world * nodes * iters * K / (ms * 1e-3)
+    mesh_value = nodes * iters * K / (ms * 1e-3)  # one global mesh at every N
 
     ctx.set_timing(True)
     mesh_step(0)
     rep = ctx.timing_report()
     ctx.set_timing(False)
-    step_ms = rep['mesh_step']['ms'] / rep['mesh_step']['n']
-    achieved = nodes * MESH_BYTES_PER_UPDATE / (step_ms * 1e-3) / 1e9
+    step_ms = max_over_ranks(rep['mesh_step']['ms'] / rep['mesh_step']['n'])
+    local_nodes = (y1 - y0) * MESH_N
+    achieved = local_nodes * MESH_BYTES_PER_UPDATE / (step_ms * 1e-3) / 1e9
 
     hx = torch.zeros(x0.shape, dtype=torch.float32, pin_memory=True).numpy()
     hp = torch.empty(prev.shape, dtype=torch.float32, pin_memory=True)
     hp.copy_(prev)
     hp = hp.numpy()
+    if world > 1:
+      chunk.close()
     torch.cuda.synchronize()
 
     def mesh_e2e(i):
-      out, e_kin, t = mesh.relax_mesh(hx, hp, cfg)
+      if world == 1:
+        out, e_kin, t = mesh.relax_mesh(hx, hp, cfg)
+      else:
+        out, e_kin, t = mesh_sharded.relax_mesh_sharded(hx, hp, cfg)
       assert t == iters and out.shape == hx.shape
 
     mesh_e2e(0)
@@ -448,21 +463,23 @@ def run_ours(args):
     result['mesh'] = {
         'metric': 'node-updates/s', 'value': mesh_value, 'unit': 'node-updates/s',
         'ms_per_step': ms / K, 'gpu_launches': launches,
-        'scaling': 'weak (replicas: one 2048^2 mesh per rank; the halo-sharded '
-                   'solver is not built yet)' if world > 1 else 'n/a',
+        'scaling': 'strong (one 2048^2 mesh, rows sharded over the ranks; device-side '
+                   'halo reads and step flags over NVLink peer memory, no collective '
+                   'inside a chunk)' if world > 1 else 'n/a',
         'config': {'workload': f'mesh.relax_mesh chunk: {iters} FIRE steps, '
                                f'[2,1,{MESH_N},{MESH_N}] fp32, k0=0.1, k=0.1, stride 40, '
                                'prefer_orig_order, prev with 1% NaN; state 134 MB > L2'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
                      'traffic': None, 'peak_source': peaks['source'],
-                     'kernel': 'mesh2d_kernel<1,true>',
+                     'kernel': 'mesh2d_kernel<1,true,%s>' % ('true' if world > 1 else 'false'),
                      'kernel_us_per_launch': step_ms * 1e3,
-                     'algorithmic_bytes_per_launch': nodes * MESH_BYTES_PER_UPDATE},
-        'e2e': {'value': world * nodes * iters * K / (e2e_ms * 1e-3),
+                     'algorithmic_bytes_per_launch': local_nodes * MESH_BYTES_PER_UPDATE,
+                     'note': 'per-GPU: bytes of the rank-local slab / its launch time'},
+        'e2e': {'value': nodes * iters * K / (e2e_ms * 1e-3),
                 'unit': 'node-updates/s',
-                'h2d_bytes_per_step': 2 * 2 * nodes * 4,
-                'd2h_bytes_per_step': 2 * nodes * 4},
+                'h2d_bytes_per_step': 2 * 2 * local_nodes * 4,
+                'd2h_bytes_per_step': 2 * local_nodes * 4},
     }
 
   # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
