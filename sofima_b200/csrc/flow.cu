@@ -589,7 +589,8 @@ __device__ __forceinline__ bool is_peak(const float* im, const PeakParams& pp, i
 // Pass 2: second peak under the batch-coupled exclusion rule + statistics.
 __global__ void __launch_bounds__(kThreads)
 peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, const int* p1a,
-             const unsigned* __restrict__ bitmap, int ndim_out, float* out) {
+             const unsigned* __restrict__ bitmap, int ndim_out, float* out,
+             const float* __restrict__ bandmax, int band_rows, int nbands) {
   __shared__ unsigned long long sm[kThreads / 32];
   __shared__ float smin[kThreads / 32];
   const long long n = (long long)pp.sz * pp.sy * pp.sx;
@@ -612,17 +613,30 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
     const unsigned long long k = peak_key(v, (unsigned)i);
     best = k > best ? k : best;
   };
-  {
+  auto scan = [&](int lo, int hi) {  // flat pixel range [lo, hi)
     constexpr int U = 8;  // independent loads in flight per thread
-    int i = threadIdx.x;
-    for (; i + (U - 1) * kThreads < n; i += U * kThreads) {
+    int i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
       float v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) v[u] = __ldg(im + i + u * kThreads);
 #pragma unroll
       for (int u = 0; u < U; ++u) consider(i + u * kThreads, v[u]);
     }
-    for (; i < n; i += kThreads) consider(i, __ldg(im + i));
+    for (; i < hi; i += kThreads) consider(i, __ldg(im + i));
+  };
+  if (bandmax != nullptr) {
+    // rows_inv_fast recorded the maximum of every band of `band_rows` rows: bands
+    // that cannot hold a pixel above the threshold are never read.
+    const float* bmx = bandmax + (long long)blockIdx.x * nbands;
+    for (int bnd = 0; bnd < nbands; ++bnd) {
+      if (!(__ldg(bmx + bnd) > thr)) continue;
+      const int lo = bnd * band_rows * pp.sx;
+      const int hi = min((int)n, lo + band_rows * pp.sx);
+      scan(lo, hi);
+    }
+  } else {
+    scan(0, (int)n);
   }
   best = block_max_key(best, sm);
 
@@ -731,7 +745,7 @@ static int make_plan(sofima_ctx* ctx, int L, FftPlan* P) {
 // keys_ready: the (max, argmax) keys and NaN flags of the batch were already
 // produced by rows_inv_fast into the "flow.keys" / "flow.nan" scratch buffers.
 static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const PeakParams& pp,
-                     float* out_peaks, bool keys_ready) {
+                     float* out_peaks, bool keys_ready, int band_rows = 0, int nbands = 0) {
   if (B == 0) return SOFIMA_OK;
   const long long n = (long long)pp.sz * pp.sy * pp.sx;
   if (n > INT32_MAX) return fail(ctx, SOFIMA_EINVAL, "correlation image too large");
@@ -760,9 +774,16 @@ static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const Pe
   SOFIMA_CHECK_LAUNCH(ctx);
   {
     LaunchTimer timer(ctx, "flow_peak2");
+    const float* bandmax = nullptr;
+    if (keys_ready && nbands > 0) {
+      void* bmx = nullptr;
+      if ((rc = scratch(ctx, "flow.bandmax", sizeof(float) * B * nbands, &bmx))) return rc;
+      bandmax = static_cast<const float*>(bmx);
+    }
     peak2_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (const float*)v1,
                                                             (const int*)p1, (const unsigned*)bm,
-                                                            pp.ndim + 2, out_peaks);
+                                                            pp.ndim + 2, out_peaks, bandmax,
+                                                            band_rows, nbands);
     SOFIMA_CHECK_LAUNCH(ctx);
   }
   return SOFIMA_OK;
@@ -826,10 +847,10 @@ static void launch_cols_fast(sofima_ctx* ctx, const Problem& P, const float2* tw
 template <int N2>
 static void launch_rows_inv_fast(sofima_ctx* ctx, const Problem& P, const float2* tw,
                                  const float2* U, float* images, float scale,
-                                 unsigned long long* keys, int* nanflag) {
+                                 unsigned long long* keys, int* nanflag, float* bandmax) {
   constexpr int TR = FastLines<N2>::n;
   rows_inv_fast<N2, TR><<<dim3(ceil_div((P.sy + 1) / 2, TR), 1, P.nb), TR * FastDims<N2>::G, 0,
-                         ctx->stream>>>(P, tw, U, images, scale, keys, nanflag);
+                         ctx->stream>>>(P, tw, U, images, scale, keys, nanflag, bandmax);
 }
 
 #define SOFIMA_N2_SWITCH(n2, CALL)          \
@@ -850,7 +871,8 @@ static void launch_rows_inv_fast(sofima_ctx* ctx, const Problem& P, const float2
 static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
                      const void* post_img, const uint8_t* pre_mask, const uint8_t* post_mask,
                      const int32_t* pre_starts, const int32_t* post_starts, long long B,
-                     float* images, bool* keys_ready) {
+                     float* images, bool* keys_ready, int* band_rows = nullptr,
+                     int* nbands = nullptr) {
   const bool masked = pre_mask != nullptr || post_mask != nullptr;
   if (keys_ready) *keys_ready = false;
   Problem P;
@@ -913,6 +935,15 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
     SOFIMA_CUDA(ctx, cudaMemsetAsync(nanf, 0, sizeof(int) * B, ctx->stream));
     *keys_ready = true;
   }
+  // Band maxima written by rows_inv_fast: one value per (pair, block of 2 TR rows).
+  void* bandmax = nullptr;
+  const int fast_tr = n2x <= 20 ? 8 : 4;  // == FastLines<N2>::n
+  const int nb_bands = fast ? ceil_div((P.sy + 1) / 2, fast_tr) : 0;
+  if (fast) {
+    if ((rc = scratch(ctx, "flow.bandmax", sizeof(float) * B * nb_bands, &bandmax))) return rc;
+    if (band_rows) *band_rows = 2 * fast_tr;
+    if (nbands) *nbands = nb_bands;
+  }
 
   // Shared-memory budgets.
   const size_t smem_cap = 200 * 1024;
@@ -967,16 +998,20 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   }
   const float scale = (float)(1.0 / ((double)Lx * (double)Ly));
 
+  if (!p->has_mean) {  // patch sums of the whole batch in one launch
+    for (long long b0 = 0; b0 < B; b0 += 65535) {
+      P.b0 = b0;
+      P.nb = (int)((B - b0 < 65535) ? (B - b0) : 65535);
+      LaunchTimer timer(ctx, "flow_mean");
+      patch_mean_kernel<<<dim3(P.nb, 2, kMeanGroups), kThreads, 0, ctx->stream>>>(
+          P, (MeanPartial*)means);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+  }
   for (long long b0 = 0; b0 < B; b0 += nsub) {
     const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
     P.b0 = b0;
     P.nb = nb;
-    if (!p->has_mean) {
-      LaunchTimer timer(ctx, "flow_mean");
-      patch_mean_kernel<<<dim3(nb, 2, kMeanGroups), kThreads, 0, ctx->stream>>>(
-          P, (MeanPartial*)means);
-      SOFIMA_CHECK_LAUNCH(ctx);
-    }
     const int rp_max = (P.PY + 1) / 2;
     if (fast) {
       {
@@ -1004,7 +1039,8 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
           kp = static_cast<unsigned long long*>(tmp);
           np = reinterpret_cast<int*>(kp + B);
         }
-#define CALL(N) launch_rows_inv_fast<N>(ctx, P, Fx.tw, (const float2*)Ubuf, images, scale, kp, np)
+#define CALL(N) \
+  launch_rows_inv_fast<N>(ctx, P, Fx.tw, (const float2*)Ubuf, images, scale, kp, np, (float*)bandmax)
         SOFIMA_N2_SWITCH(n2x, CALL)
 #undef CALL
         SOFIMA_CHECK_LAUNCH(ctx);
@@ -1245,15 +1281,17 @@ int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void
   if ((rc = scratch(ctx, "flow.images", sizeof(float) * (size_t)batch * img_elems, &images)))
     return rc;
   bool keys_ready = false;
+  int band_rows = 0, nbands = 0;
   if (p->ndim == 3)
     rc = flow::run_xcorr3(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
                           post_starts, batch, static_cast<float*>(images));
   else
     rc = flow::run_xcorr(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
-                         post_starts, batch, static_cast<float*>(images), &keys_ready);
+                         post_starts, batch, static_cast<float*>(images), &keys_ready,
+                         &band_rows, &nbands);
   if (rc) return rc;
   return flow::run_peaks(ctx, static_cast<const float*>(images), batch, pp, out_peaks,
-                         keys_ready);
+                         keys_ready, band_rows, nbands);
 }
 
 int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img, const int64_t* img_shape,

@@ -242,7 +242,7 @@ template <int N2, int TR>
 __global__ void __launch_bounds__(TR * FastDims<N2>::G)
 rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ U,
               float* __restrict__ images, float scale, unsigned long long* keys,
-              int* nanflag) {
+              int* nanflag, float* __restrict__ bandmax) {
   using D = FastDims<N2>;
   constexpr int L = D::L;
   __shared__ float2 ex[TR * D::EX];
@@ -325,6 +325,11 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
   if (threadIdx.x == 0) {
     for (int w = 1; w < (NT + 31) / 32; ++w) best = kred[w] > best ? kred[w] : best;
     atomicMax(&keys[P.b0 + blockIdx.z], best);
+    // maximum of this band of 2 TR rows (NaN never compares above a threshold)
+    float bv = -INFINITY;
+    unsigned bi;
+    if (best != 0) key_decode(best, &bv, &bi);
+    bandmax[(P.b0 + blockIdx.z) * gridDim.x + blockIdx.x] = bv;
   }
 }
 
