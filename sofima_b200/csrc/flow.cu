@@ -18,6 +18,7 @@
 // footprint is sized well below the 126 MB L2.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -965,11 +966,16 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_cap));
 
-  // Sub-batches: keep T and U (and the six masked outputs) L2-resident.
+  // Sub-batches of at most `scratch_mb` of spectra (T, U and the six masked outputs).
   const size_t per_pair = sizeof(float2) * ((size_t)P.nslots * P.PY * P.nkx +
                                             (size_t)pr.nout * P.sy * P.nkx) +
                           (masked ? sizeof(float) * 6 * (size_t)P.sy * P.sx : 0);
-  long long nsub = (long long)((96ull << 20) / per_pair);
+  // Sub-batches bound the scratch memory only; measured on B200 the pipeline is fastest
+  // when a whole reference batch (1024 pairs = 0.84 GB of spectra) goes through each
+  // stage in one launch -- streaming T / U through HBM costs less than small grids.
+  size_t scratch_mb = 1536;
+  if (const char* e = getenv("SOFIMA_FLOW_SCRATCH_MB")) scratch_mb = (size_t)atoi(e);
+  long long nsub = (long long)((scratch_mb << 20) / per_pair);
   if (nsub < 1) nsub = 1;
   if (nsub > B) nsub = B;
   if (nsub > 65535) nsub = 65535;
