@@ -265,7 +265,7 @@ def run_reference(args):
                'e2e': {'value': mesh_v, 'unit': 'node-updates/s',
                        'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}},
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 # ----------------------------------------------------------------------------------
@@ -335,9 +335,9 @@ def run_ours(args):
       pre, post, _ = tiles[i % npairs_tiles]
       job.run(pre, post, out=out_d)
 
-    for i in range(W):
-      flow_step(i)
-    with ClockSampler(local) as cs:
+    with ClockSampler(local) as cs:  # sampled under load: warm-up + timed region
+      for i in range(W):
+        flow_step(i)
       ms, launches = timed(flow_step, K)
     clocks['flow'] = cs.summary()
     pairs_per_step = g * g
@@ -423,9 +423,9 @@ def run_ours(args):
       dt, alpha, _, cap, _, _ = chunk.run(state['dt'], state['alpha'], state['cap'])
       state.update(dt=float(dt), alpha=float(alpha), cap=float(cap))
 
-    for i in range(W):
-      mesh_step(i)
     with ClockSampler(local) as cs:
+      for i in range(W):
+        mesh_step(i)
       ms, launches = timed(mesh_step, K)
     clocks['mesh'] = cs.summary()
     mesh_value = nodes * iters * K / (ms * 1e-3)  # one global mesh at every N
@@ -516,12 +516,32 @@ def run_ours(args):
     if args.path == 'mesh':
       line['config'] = result.pop('config')
     line.update(result)
-    print(json.dumps(line))
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+  """Libraries (NCCL banner, torchrun) must not write to stdout: the contract is ONE
+  JSON line there.  fd 1 is pointed at stderr; emit() writes to the saved fd."""
+  global _REAL_STDOUT
+  if _REAL_STDOUT is None:
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+  out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+  out.write(json.dumps(line) + '\n')
+  out.flush()
+
+
 def main():
+  _protect_stdout()
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=5)
