@@ -44,6 +44,15 @@ DENSE_FLOP_PER_PAIR = 2.0 * PATCH**4          # p^4 MAC per patch p
 MESH_BYTES_PER_UPDATE = 56.0                  # 8 floats in, 6 out
 
 
+def _traffic(kernel):
+  """DRAM bytes per launch of `kernel` from the committed ncu --set full capture."""
+  path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+  try:
+    return json.load(open(path))[kernel]['bytes_per_launch']
+  except (OSError, KeyError, ValueError):
+    return None
+
+
 def _peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -386,7 +395,8 @@ def run_ours(args):
         'ms_per_step': ms / K, 'gpu_launches': launches,
         'roofline': {
             'bound': 'tensor', 'achieved': achieved_tf, 'peak': peaks['tflops'],
-            'unit': 'TFLOP/s', 'frac': achieved_tf / peaks['tflops'], 'traffic': None,
+            'unit': 'TFLOP/s', 'frac': achieved_tf / peaks['tflops'],
+            'traffic': _traffic('flow_cols'),
             'peak_source': peaks['source'] + ', bf16 sustained',
             'note': 'dense-equivalent: 2*160^4 FLOP per patch pair (SURVEY 8d) over '
                     'the summed device time of the flow kernels of one step; the work '
@@ -471,7 +481,8 @@ def run_ours(args):
                                'prefer_orig_order, prev with 1% NaN; state 134 MB > L2'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
-                     'traffic': None, 'peak_source': peaks['source'],
+                     'traffic': _traffic('mesh2d_kernel') if local_nodes == MESH_N * MESH_N else None,
+                     'peak_source': peaks['source'],
                      'kernel': 'mesh2d_kernel<1,true,%s>' % ('true' if world > 1 else 'false'),
                      'kernel_us_per_launch': step_ms * 1e3,
                      'algorithmic_bytes_per_launch': local_nodes * MESH_BYTES_PER_UPDATE,
