@@ -122,6 +122,47 @@ typedef struct {
   int32_t pad;
 } sofima_mesh_state;
 
+/* ---- Elastic tile stitching: the per-step target mesh ("prev_fn") -------------
+ * Replaces stitch_elastic.compute_target_mesh vmapped over all tiles
+ * (stitch_elastic.py:624-676, _update_mesh :573-620, _apply_flow :456-570,
+ * map_utils.compose_maps_fast map_utils.py:616-734 with mode='constant'), i.e. the
+ * `prev_fn` closure of notebooks/em_stitching.ipynb:545-549.  All pointers are
+ * device pointers. */
+typedef struct {
+  const float* fx;      /* [2, ntiles, fx_ny, fx_nx] flows between horizontal neighbours */
+  const float* fy;      /* [2, ntiles, fy_ny, fy_nx] flows between vertical neighbours */
+  const int32_t* nbors; /* [ntiles, 4, 8] NeighborInfo table (stitch_elastic.py:43-72) */
+  int64_t fx_ny, fx_nx, fy_ny, fy_nx;
+  double stride[2];     /* yx stride of the mesh / flow grids in pixels */
+} sofima_stitch_target;
+
+/* out[2, ntiles, ny, nx] = target mesh of every tile for the tile meshes
+ * x[2, ntiles, ny, nx] (shape->nb = ntiles, shape->nz = 1). */
+int sofima_stitch_target_mesh(sofima_ctx* ctx, const float* x,
+                              const sofima_mesh_shape* shape,
+                              const sofima_stitch_target* target, float* out);
+
+/* sofima_mesh_chunk for mesh.relax_mesh(x, None, config, prev_fn=...) with the
+ * stitching prev_fn: `prev` is re-evaluated on the device from the advanced
+ * positions inside every step (mesh.py:429-430), in-plane force only. */
+int sofima_mesh_chunk_stitch(sofima_ctx* ctx, float* x, float* v, float* a,
+                             const sofima_stitch_target* target,
+                             const sofima_mesh_shape* shape,
+                             const sofima_integration_config* cfg, float* dt,
+                             float* alpha, float* cap, int32_t* n_pos,
+                             double* e_kin, float* v_max);
+
+/* Replaces map_utils.compose_maps_fast (map_utils.py:616-734): out = map2(map1(p))
+ * on the grid of map1, relative format, bilinear (jax map_coordinates order 1).
+ *   dim 2: map1 [2, z, y1, x1], map2 [2, z, y2, x2]; dim 3: [3, z, y, x] each
+ *   shape1/shape2: zyx extents (3 values); start1/2, stride1/2: the last `dim` axes, zyx
+ *   constant_mode: 0 = mode 'nearest', 1 = mode 'constant' with cval NaN */
+int sofima_compose_maps(sofima_ctx* ctx, int dim, const float* map1,
+                        const int64_t* shape1, const int64_t* start1,
+                        const double* stride1, const float* map2,
+                        const int64_t* shape2, const int64_t* start2,
+                        const double* stride2, int constant_mode, float* out);
+
 /* Same, without the final synchronisation: a sofima_mesh_state is copied to the
  * pinned host block `results_pinned` when the stream reaches that point.  Used to
  * queue many chunks back to back. */

@@ -119,6 +119,14 @@ class MeshState(ctypes.Structure):
               ('v_max', ctypes.c_float), ('pad', ctypes.c_int32)]
 
 
+class StitchTargetPod(ctypes.Structure):
+  _fields_ = [('fx', ctypes.c_void_p), ('fy', ctypes.c_void_p),
+              ('nbors', ctypes.c_void_p),
+              ('fx_ny', ctypes.c_int64), ('fx_nx', ctypes.c_int64),
+              ('fy_ny', ctypes.c_int64), ('fy_nx', ctypes.c_int64),
+              ('stride', ctypes.c_double * 2)]
+
+
 class XcorrParams(ctypes.Structure):
   _fields_ = [
       ('ndim', ctypes.c_int32), ('img_dtype', ctypes.c_int32),
@@ -155,6 +163,19 @@ _PROTOS = {
         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
         ctypes.POINTER(ctypes.c_float)]),
+    'sofima_mesh_chunk_stitch': (ctypes.c_int, [
+        _vp, _vp, _vp, _vp, ctypes.POINTER(StitchTargetPod), ctypes.POINTER(MeshShape),
+        ctypes.POINTER(IntegrationConfigPod), ctypes.POINTER(ctypes.c_float),
+        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
+        ctypes.POINTER(ctypes.c_float)]),
+    'sofima_stitch_target_mesh': (ctypes.c_int, [
+        _vp, _vp, ctypes.POINTER(MeshShape), ctypes.POINTER(StitchTargetPod), _vp]),
+    'sofima_compose_maps': (ctypes.c_int, [
+        _vp, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64),
+        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double), _vp,
+        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+        ctypes.POINTER(ctypes.c_double), ctypes.c_int, _vp]),
     'sofima_mesh_chunk_async': (ctypes.c_int, [
         _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.POINTER(MeshShape),
         ctypes.POINTER(IntegrationConfigPod), ctypes.c_float, ctypes.c_float,

@@ -1,0 +1,76 @@
+"""Drop-in for the device-side part of `sofima.map_utils` (reference map_utils.py).
+
+  compose_maps_fast        map_utils.py:616-734
+
+Coordinate maps are in the reference's relative format `[2 or 3, z, y, x]`.  NumPy
+in -> NumPy out, CUDA torch tensors stay on the device.  The bilinear sampling
+follows `jax.scipy.ndimage.map_coordinates(order=1)` operation by operation
+(csrc/stitch.cuh); there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import collections.abc
+import ctypes
+from typing import Sequence
+
+import numpy as np
+
+from . import _native
+from . import mesh as _mesh
+
+
+def _as_vec(value, dim: int):
+  if not isinstance(value, collections.abc.Sequence) and not isinstance(value, np.ndarray):
+    return (value,) * dim
+  assert len(value) == dim, f'Dimension mismatch: {value=} vs {dim=}'
+  return tuple(value)
+
+
+def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,
+                      start2: Sequence[float], stride2, mode='nearest'):
+  """Composes two coordinate maps: map2(map1(z, y, x)) on the grid of map1.
+
+  Same contract as map_utils.compose_maps_fast (map_utils.py:616-734): invalid
+  (NaN) values in either map are NOT interpolated.
+
+  Args:
+    map1: [2 or 3, z, y, x] 1st coordinate map in relative format
+    start1: [z]yx origin coordinates for map1 (longer sequences: the last entries)
+    stride1: distance between nearest neighbors of map1 (scalar or [z]yx)
+    map2, start2, stride2: same for the 2nd map
+    mode: 'nearest' or 'constant' (cval NaN), as passed to map_coordinates
+
+  Returns:
+    [2 or 3, z, y, x] composed map covering the area of map1 (with stride1)
+  """
+  assert map1.shape[0] == map2.shape[0]
+  dim = int(map1.shape[0])
+  if dim not in (2, 3) or len(map1.shape) != 4 or len(map2.shape) != 4:
+    raise ValueError('maps must be [2 or 3, z, y, x]')
+  if mode not in ('nearest', 'constant'):
+    raise NotImplementedError(f"mode {mode!r}: only 'nearest' and 'constant' are built")
+  stride1 = _as_vec(stride1, dim)
+  stride2 = _as_vec(stride2, dim)
+  s1 = [int(v) for v in np.asarray(start1).reshape(-1)[-dim:]]
+  s2 = [int(v) for v in np.asarray(start2).reshape(-1)[-dim:]]
+  if len(s1) != dim or len(s2) != dim:
+    raise ValueError('start1 / start2 need at least `dim` entries')
+  if dim == 2 and map1.shape[1] != map2.shape[1]:
+    raise ValueError('2-d maps need the same number of sections')
+
+  dev = map1.device.index if _mesh._is_tensor(map1) and map1.is_cuda else None
+  ctx = _native.Context.get(dev)
+  m1 = _mesh._to_device(map1, ctx, copy=False)
+  m2 = _mesh._to_device(map2, ctx, copy=False)
+  out = _mesh._torch().empty_like(m1)
+  i64x3 = ctypes.c_int64 * 3
+  ctx.bind_stream()
+  rc = _native.lib().sofima_compose_maps(
+      ctx.handle, dim, m1.data_ptr(), i64x3(*m1.shape[1:]), (ctypes.c_int64 * dim)(*s1),
+      (ctypes.c_double * dim)(*[float(v) for v in stride1]), m2.data_ptr(),
+      i64x3(*m2.shape[1:]), (ctypes.c_int64 * dim)(*s2),
+      (ctypes.c_double * dim)(*[float(v) for v in stride2]),
+      int(mode == 'constant'), out.data_ptr())
+  _native.check(ctx.handle, rc)
+  return _mesh._from_device(out, map1)

@@ -242,7 +242,7 @@ def _config_pod(config: IntegrationConfig, kind: int) -> _native.IntegrationConf
 class _Chunk:
   """Device-resident solver state for repeated velocity_verlet calls."""
 
-  def __init__(self, x, v, prev, config: IntegrationConfig, kind: int):
+  def __init__(self, x, v, prev, config: IntegrationConfig, kind: int, prev_fn=None):
     like = x
     dev = x.device.index if _is_tensor(x) and x.is_cuda else None
     self.ctx = _native.Context.get(dev)
@@ -260,6 +260,9 @@ class _Chunk:
     self.shape = _shape_pod(tuple(self.x.shape), kind)
     self.pod = _config_pod(config, kind)
     self.config = config
+    self.target = None
+    if prev_fn is not None:
+      self.target = _stitch_target(prev_fn, kind, tuple(self.x.shape), self.ctx)
 
   def run(self, dt: float, alpha: float, cap: float):
     """One velocity_verlet call.  Returns (dt, alpha, n_pos, cap, e_kin, v_max)."""
@@ -267,6 +270,15 @@ class _Chunk:
                             ctypes.c_float(cap))
     n_pos, e_kin, v_max = ctypes.c_int32(0), ctypes.c_double(0), ctypes.c_float(0)
     self.ctx.bind_stream()
+    if self.target is not None:
+      rc = _native.lib().sofima_mesh_chunk_stitch(
+          self.ctx.handle, self.x.data_ptr(), self.v.data_ptr(), self.a.data_ptr(),
+          ctypes.byref(self.target), ctypes.byref(self.shape), ctypes.byref(self.pod),
+          ctypes.byref(c_dt), ctypes.byref(c_alpha), ctypes.byref(c_cap),
+          ctypes.byref(n_pos), ctypes.byref(e_kin), ctypes.byref(v_max))
+      _native.check(self.ctx.handle, rc)
+      return (np.float32(c_dt.value), np.float32(c_alpha.value), int(n_pos.value),
+              np.float32(c_cap.value), float(e_kin.value), np.float32(v_max.value))
     rc = _native.lib().sofima_mesh_chunk(
         self.ctx.handle, self.kind, self.x.data_ptr(), self.v.data_ptr(),
         self.a.data_ptr(), None if self.prev is None else self.prev.data_ptr(),
@@ -278,11 +290,20 @@ class _Chunk:
             np.float32(c_cap.value), float(e_kin.value), np.float32(v_max.value))
 
 
-def _reject_prev_fn(prev_fn):
-  if prev_fn is not None:
+def _stitch_target(prev_fn, kind: int, x_shape, ctx):
+  """C-ABI descriptor of a device-side prev_fn (stitch_elastic.StitchTarget)."""
+  describe = getattr(prev_fn, '_sofima_device_target', None)
+  if describe is None:
     raise NotImplementedError(
-        'prev_fn (per-step target meshes, stitch_elastic.compute_target_mesh) '
-        'is not part of the CUDA backend yet; pass a fixed `prev` array.')
+        'The CUDA backend evaluates prev_fn inside the step kernel sequence, so it '
+        'must be a device-side target description: build it with '
+        'sofima_b200.stitch_elastic.target_mesh_fn(nbors, fx, fy, stride) (the '
+        'stitching prev_fn of stitch_elastic.compute_target_mesh); arbitrary Python '
+        f'callables such as {prev_fn!r} cannot be traced into it.')
+  if kind != _INPLANE:
+    raise NotImplementedError(
+        'prev_fn with the 3-d mesh force is not part of the CUDA backend yet.')
+  return describe(x_shape, ctx)
 
 
 def velocity_verlet(x, v, prev, config: IntegrationConfig, force_cap: float,
@@ -294,9 +315,10 @@ def velocity_verlet(x, v, prev, config: IntegrationConfig, force_cap: float,
   `(x, v, a)` or, with FIRE, `(x, v, a, dt, alpha, n_pos, cap)`.  Inputs are not
   modified.
   """
-  _reject_prev_fn(prev_fn)
+  if prev is not None and prev_fn is not None:
+    raise ValueError('Only one of: "prev" and "prev_fn" can be specified.')
   kind = _force_kind(mesh_force)
-  chunk = _Chunk(x, v, prev, config, kind)
+  chunk = _Chunk(x, v, prev, config, kind, prev_fn)
   dt = config.dt if fire_dt is None else fire_dt
   alpha = config.alpha if fire_alpha is None else fire_alpha
   dt, alpha, n_pos, cap, _, _ = chunk.run(float(dt), float(alpha), float(force_cap))
@@ -316,7 +338,8 @@ def relax_mesh(x, prev, config: IntegrationConfig, mesh_force=inplane_force,
       due to 0-length springs
     config: simulation parameters
     mesh_force: `inplane_force` or `elastic_mesh_3d` of this module
-    prev_fn: not supported by the CUDA backend yet
+    prev_fn: optional device-side target description replacing `prev`, see
+      `stitch_elastic.target_mesh_fn` (the reference takes a JAX callable here)
 
   Returns:
     tuple of: updated mesh positions, kinetic energy history, number of
@@ -339,10 +362,9 @@ def relax_mesh(x, prev, config: IntegrationConfig, mesh_force=inplane_force,
 
   if prev is not None and prev_fn is not None:
     raise ValueError('Only one of: "prev" and "prev_fn" can be specified.')
-  _reject_prev_fn(prev_fn)
 
   kind = _force_kind(mesh_force)
-  chunk = _Chunk(x, None, prev, config, kind)  # state stays on the device
+  chunk = _Chunk(x, None, prev, config, kind, prev_fn)  # state stays on the device
 
   while t < config.max_iters:
     dt_n, alpha_n, n_pos, cap_n, ek, v_max = chunk.run(

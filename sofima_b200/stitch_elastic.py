@@ -1,0 +1,201 @@
+"""Drop-in for the solver-facing part of `sofima.stitch_elastic` (reference
+stitch_elastic.py): the per-step target mesh of elastic tile stitching.
+
+  NeighborInfo             stitch_elastic.py:43-72
+  aggregate_arrays         stitch_elastic.py:285-453   (host, NumPy -- as in the reference)
+  compute_target_mesh      stitch_elastic.py:624-676   (CUDA, csrc/stitch.cuh)
+  target_mesh_fn           the `prev_fn` closure the notebooks build around it
+                           (notebooks/em_stitching.ipynb:545-549)
+
+The reference's `prev_fn` is a JAX callable traced into the jitted integrator; here it
+is a device-side description (`StitchTarget`) that `mesh.relax_mesh(..., prev_fn=...)`
+hands to the C ABI, which re-evaluates the target inside every integration step.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import enum
+from typing import Mapping, Sequence
+
+import numpy as np
+
+from . import _native
+from . import mesh as _mesh
+
+
+class NeighborInfo(enum.IntEnum):
+  """Indices into a neighbour-info row (stitch_elastic.py:43-72)."""
+  nbor_idx = 0             # neighbouring tile index
+  flow_idx = 1             # index within the flow array
+  coarse_offset_ortho = 2  # coarse offset orthogonal to the overlap dim (pixels)
+  flow_size_ortho = 3      # flow extent orthogonal to the overlap dim
+  flow_size_overlap = 4    # flow extent along the overlap dim
+  fine_off_x = 5           # offset vector used when the flow was computed
+  fine_off_y = 6
+  dim = 7                  # 0: x neighbour, 1: y neighbour
+  coarse_offset_z = 8      # 3-d meshes only
+  flow_size_z = 9
+  fine_off_z = 10
+
+
+def aggregate_arrays(x_data, y_data, tile_coords: Sequence[tuple[int, int]],
+                     coarse_mesh: np.ndarray, stride: Sequence[float],
+                     tile_shape: Sequence[int]):
+  """Aggregates the per-pair flow fields of a tile grid into dense arrays.
+
+  Same contract as stitch_elastic.aggregate_arrays (stitch_elastic.py:285-453).
+
+  Args:
+    x_data: (coarse offsets [2 or 3, ty, tx] between (x, y) and (x+1, y); dict
+      tile -> fine flow; dict tile -> offset vector used for the fine flow)
+    y_data: the same for (x, y) and (x, y+1)
+    tile_coords: (x, y) tile coordinates
+    coarse_mesh: [2 or 3, ty, tx] rigid solution (initial tile positions)
+    stride: [z]yx stride of mesh and flow grids in pixels
+    tile_shape: [z]yx tile shape in pixels
+
+  Returns:
+    fx [dim, N, ...], fy [dim, N, ...] NaN-padded flows; x [dim, N, ...] initial
+    meshes; nbors [N, 4, 8 or 11] int NeighborInfo table; dict tile -> index
+  """
+  cx, fine_x, offsets_x = x_data
+  cy, fine_y, offsets_y = y_data
+  assert cx.ndim == 3 and cy.ndim == 3
+  index = {tuple(c): i for i, c in enumerate(tile_coords)}
+  dim = len(stride)
+  ntiles = len(index)
+
+  def dense(fine: Mapping[tuple[int, int], np.ndarray]) -> np.ndarray:
+    extent = np.ones(dim, dtype=int)
+    for f in fine.values():
+      extent = np.maximum(extent, f.shape[1:])
+    arr = np.full((dim, ntiles) + tuple(int(e) for e in extent), np.nan)
+    for key, i in index.items():
+      f = fine.get(key)
+      if f is not None:
+        arr[(slice(None), i) + tuple(slice(0, s) for s in f.shape[1:])] = f[:dim]
+    return arr
+
+  fx, fy = dense(fine_x), dense(fine_y)
+
+  def row(nbor_key, flow_key, coarse, fine, offsets, axis):
+    shape = fine[flow_key].shape
+    ortho, overlap = shape[-2], shape[-1]
+    if axis == 1:
+      ortho, overlap = overlap, ortho
+    off = offsets[flow_key]
+    vals = [index[nbor_key], index[flow_key], coarse[1] if axis == 0 else coarse[0],
+            ortho, overlap, off[0], off[1], axis]
+    if dim == 3:
+      vals += [coarse[2], shape[-3], off[2]]
+    return vals
+
+  nbors = np.full((ntiles, 4, 8 if dim == 2 else 11), -1, dtype=int)
+  for tx, ty in tile_coords:
+    i = index[tx, ty]
+    if (tx - 1, ty) in fine_x:   # left neighbour: its flow, we are the 'post' tile
+      nbors[i, 0] = row((tx - 1, ty), (tx - 1, ty), cx[:, ty, tx - 1], fine_x, offsets_x, 0)
+    if (tx, ty) in fine_x:       # right neighbour: our flow
+      nbors[i, 1] = row((tx + 1, ty), (tx, ty), cx[:, ty, tx], fine_x, offsets_x, 0)
+    if (tx, ty - 1) in fine_y:   # neighbour above
+      nbors[i, 2] = row((tx, ty - 1), (tx, ty - 1), cy[:, ty - 1, tx], fine_y, offsets_y, 1)
+    if (tx, ty) in fine_y:       # neighbour below
+      nbors[i, 3] = row((tx, ty + 1), (tx, ty), cy[:, ty, tx], fine_y, offsets_y, 1)
+
+  mesh_shape = [int(s) for s in (np.array(tile_shape) // np.array(stride))]
+  x = np.zeros([dim, ntiles] + mesh_shape, dtype=np.float32)
+  for tx, ty in tile_coords:
+    x[:, index[tx, ty]] = np.asarray(coarse_mesh[:, ty, tx]).reshape((dim,) + (1,) * dim)
+  return fx, fy, x, nbors, index
+
+
+class StitchTarget:
+  """Device-side `prev_fn` for elastic stitching.
+
+  Calling it evaluates the target mesh of every tile for the tile meshes `x`
+  ([2, N, y, x]) -- what the notebooks' `prev_fn` returns.  Passed as
+  `mesh.relax_mesh(x, None, config, prev_fn=target)` the same computation runs inside
+  the integrator, before every force evaluation (mesh.py:429-430).
+  """
+
+  def __init__(self, nbors, fx, fy, stride: Sequence[float] = (20, 20)):
+    nbors = np.asarray(nbors)
+    if nbors.ndim != 3 or nbors.shape[1] != 4:
+      raise ValueError(f'nbors must be [n, 4, 8 or 11], got {nbors.shape}')
+    self.dim = len(stride)
+    if self.dim != 2 or nbors.shape[2] != 8:
+      raise NotImplementedError(
+          'The CUDA stitching target is built for 2-d tile meshes ([n, 4, 8] neighbour '
+          'tables); 3-d (LICONN) stitching targets are not part of the backend yet.')
+    n = nbors.shape[0]
+    if np.any(nbors[:, :, 0] < -1) or np.any(nbors[:, :, 0] >= n) or np.any(
+        (nbors[:, :, 0] >= 0) & ((nbors[:, :, 1] < 0) | (nbors[:, :, 1] >= n))):
+      raise ValueError('neighbour / flow indices out of range')
+    self.ntiles = n
+    self.stride = tuple(float(s) for s in stride)
+    self._nbors_host = np.ascontiguousarray(nbors, dtype=np.int32)
+    self._fx_in, self._fy_in = fx, fy
+    for f in (fx, fy):
+      if len(f.shape) != 4 or f.shape[0] != 2 or f.shape[1] != n:
+        raise ValueError(f'flow arrays must be [2, {n}, y, x], got {tuple(f.shape)}')
+    self._dev = {}  # device index -> (fx, fy, nbors) tensors
+
+  def _arrays(self, ctx):
+    arrs = self._dev.get(ctx.device)
+    if arrs is None:
+      torch = _mesh._torch()
+      arrs = (_mesh._to_device(self._fx_in, ctx, copy=False),
+              _mesh._to_device(self._fy_in, ctx, copy=False),
+              torch.from_numpy(self._nbors_host).to(torch.device('cuda', ctx.device)))
+      self._dev[ctx.device] = arrs
+    return arrs
+
+  def _sofima_device_target(self, x_shape, ctx) -> _native.StitchTargetPod:
+    if len(x_shape) != 4 or x_shape[0] != 2 or x_shape[1] != self.ntiles:
+      raise ValueError(f'x must be [2, {self.ntiles}, y, x], got {tuple(x_shape)}')
+    fx, fy, nb = self._arrays(ctx)
+    pod = _native.StitchTargetPod()
+    pod.fx, pod.fy, pod.nbors = fx.data_ptr(), fy.data_ptr(), nb.data_ptr()
+    pod.fx_ny, pod.fx_nx = fx.shape[2], fx.shape[3]
+    pod.fy_ny, pod.fy_nx = fy.shape[2], fy.shape[3]
+    pod.stride[0], pod.stride[1] = self.stride
+    return pod
+
+  def __call__(self, x):
+    dev = x.device.index if _mesh._is_tensor(x) and x.is_cuda else None
+    ctx = _native.Context.get(dev)
+    xd = _mesh._to_device(x, ctx, copy=False)
+    pod = self._sofima_device_target(tuple(xd.shape), ctx)
+    shape = _native.MeshShape(2, xd.shape[1], 1, xd.shape[2], xd.shape[3])
+    out = _mesh._torch().empty_like(xd)
+    ctx.bind_stream()
+    rc = _native.lib().sofima_stitch_target_mesh(
+        ctx.handle, xd.data_ptr(), ctypes.byref(shape), ctypes.byref(pod), out.data_ptr())
+    _native.check(ctx.handle, rc)
+    return _mesh._from_device(out, x)
+
+
+def target_mesh_fn(nbors, fx, fy, stride: Sequence[float] = (20, 20)) -> StitchTarget:
+  """`prev_fn` for `mesh.relax_mesh`: vmap(compute_target_mesh)(nbors) on the device."""
+  return StitchTarget(nbors, fx, fy, stride)
+
+
+def compute_target_mesh(nbor_data, x, fx, fy, stride: Sequence[float] = (20, 20)):
+  """Target mesh of ONE tile (stitch_elastic.py:624-676).
+
+  Args:
+    nbor_data: [4, 8] neighbour info of the tile; -1 in the nbor and flow indices
+      marks missing entries
+    x: [2, n, y, x] node positions of all tiles
+    fx, fy: [2, n, y, x] flows between horizontal / vertical neighbours
+    stride: yx stride of flow and mesh data
+
+  Returns:
+    [2, y, x] target positions (NaN where no neighbour provides one)
+  """
+  nbor_data = np.asarray(nbor_data)
+  n = x.shape[1]
+  table = np.full((n,) + nbor_data.shape, -1, dtype=int)
+  table[0] = nbor_data
+  return StitchTarget(table, fx, fy, stride)(x)[:, 0]

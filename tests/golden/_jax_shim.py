@@ -157,10 +157,18 @@ def _build_jnp():
                'minimum', 'maximum', 'sum', 'max', 'min', 'argmax',
                'take_along_axis', 'isinf', 'isnan', 'round', 'fmax', 'square',
                'logical_not', 'ones', 'zeros', 'abs', 'cumsum', 'stack',
-               'concatenate', 'floor', 'ceil', 'arange', 'meshgrid', 'full'):
+               'concatenate', 'floor', 'ceil', 'arange', 'meshgrid', 'full', 'transpose'):
     setattr(jnp, name, _lift(getattr(np, name)))
   jnp.array = _array
   jnp.asarray = _array
+  jnp.full = lambda shape, fill, dtype=None: _wrap(np.full(shape, fill, dtype=dtype))
+
+  class _R:
+
+    def __getitem__(self, items):
+      return _wrap(np.r_[tuple(np.asarray(_unwrap(i)) for i in items)])
+
+  jnp.r_ = _R()
   jnp.mean = _mean
   jnp.nanmean = _nanmean
   jnp.clip = _clip
@@ -221,6 +229,78 @@ def _dynamic_slice(operand, start_indices, slice_sizes):
   return _wrap(operand[tuple(sel)])
 
 
+def _dynamic_update_slice(operand, update, start_indices):
+  operand = np.array(_unwrap(operand), copy=True)
+  update = np.asarray(_unwrap(update))
+  sel = []
+  for st, sz, n in zip(start_indices, update.shape, operand.shape):
+    st = int(min(max(int(st), 0), n - int(sz)))
+    sel.append(slice(st, st + int(sz)))
+  operand[tuple(sel)] = update
+  return _wrap(operand)
+
+
+def _dynamic_index_in_dim(operand, index, axis=0, keepdims=True):
+  operand = _unwrap(operand)
+  n = operand.shape[axis]
+  index = int(index)
+  if index < 0:
+    index += n
+  index = min(max(index, 0), n - 1)
+  out = np.take(operand, [index] if keepdims else index, axis=axis)
+  return _wrap(out)
+
+
+def _cond(pred, true_fn, false_fn, *operands):
+  return true_fn(*operands) if bool(pred) else false_fn(*operands)
+
+
+def _scan(f, init, xs):
+  carry, ys = init, []
+  for x in xs:
+    carry, y = f(carry, x)
+    ys.append(y)
+  return carry, ys
+
+
+def _map_coordinates(input, coordinates, order, mode='constant', cval=0.0):  # pylint: disable=redefined-builtin
+  """jax.scipy.ndimage.map_coordinates, order 1, modes 'constant' / 'nearest', as
+  published in jax/_src/scipy/ndimage.py: explicit per-point loops in fp32."""
+  assert order == 1 and mode in ('constant', 'nearest')
+  inp = np.asarray(_unwrap(input), dtype=np.float32)
+  coords = [np.asarray(_unwrap(c), dtype=np.float32) for c in coordinates]
+  out = np.empty(coords[0].shape, np.float32)
+  nd = inp.ndim
+  f32 = np.float32
+  with np.errstate(invalid='ignore'):
+    for pos in np.ndindex(*coords[0].shape):
+      axes = []
+      for d in range(nd):
+        c = coords[d][pos]
+        lo = np.floor(c)
+        uw = f32(c - lo)
+        lw = f32(f32(1.0) - uw)
+        i0 = int(lo) if np.isfinite(lo) and abs(lo) < 2**31 else -10**9
+        axes.append(((i0, lw), (i0 + 1, uw)))
+      acc = None
+      corners = [[]]
+      for d in range(nd):  # itertools.product order: last axis fastest
+        corners = [c + [k] for c in corners for k in (0, 1)]
+      for corner in corners:
+        w, ok, idx = None, True, []
+        for d, k in enumerate(corner):
+          i, wd = axes[d][k]
+          if mode == 'constant' and not 0 <= i < inp.shape[d]:
+            ok = False
+          idx.append(min(max(i, 0), inp.shape[d] - 1))
+          w = wd if w is None else f32(w * wd)
+        val = inp[tuple(idx)] if ok else f32(cval)
+        term = f32(w * val)
+        acc = term if acc is None else f32(acc + term)
+      out[pos] = acc
+  return _wrap(out)
+
+
 def _conv_patches(lhs, filter_shape, window_strides, padding):
   """[b, 1, *sp] -> [b, prod(filter_shape), *sp]; SAME = zero padding."""
   lhs = _unwrap(lhs)
@@ -259,7 +339,17 @@ def install():
   lax.fori_loop = _fori_loop
   lax.dynamic_slice = _dynamic_slice
   lax.conv_general_dilated_patches = _conv_patches
+  lax.dynamic_update_slice = _dynamic_update_slice
+  lax.dynamic_index_in_dim = _dynamic_index_in_dim
+  lax.cond = _cond
+  lax.scan = _scan
   jax.lax = lax
+  jscipy = types.ModuleType('jax.scipy')
+  jndimage = types.ModuleType('jax.scipy.ndimage')
+  jndimage.map_coordinates = _map_coordinates
+  jscipy.ndimage = jndimage
+  jax.scipy = jscipy
+  sys.modules.update({'jax.scipy': jscipy, 'jax.scipy.ndimage': jndimage})
   tree_util = types.ModuleType('jax.tree_util')
   tree_util.register_dataclass = lambda *a, **k: None
   jax.tree_util = tree_util
@@ -293,6 +383,12 @@ def install():
   utils = types.ModuleType('connectomics.common.utils')
   utils.batch = flow_oracle.batch
   common.geom_utils, common.utils = geom, utils
+  # bounding_box: only the class is needed (type annotations, tests' start/size).
+  from sofima_b200 import compat  # pylint: disable=g-import-not-at-top
+  bbox = types.ModuleType('connectomics.common.bounding_box')
+  bbox.BoundingBox = compat.BoundingBox
+  common.bounding_box = bbox
+  sys.modules['connectomics.common.bounding_box'] = bbox
   conn.common = common
   sys.modules.update({'connectomics': conn, 'connectomics.common': common,
                       'connectomics.common.geom_utils': geom,

@@ -237,7 +237,153 @@ def flow_cases(ff):
   return out
 
 
+def stitch_cases(mu, se):
+  """compose_maps_fast (map_utils.py:616-734) and the stitching target mesh
+  (stitch_elastic.py:285-676: aggregate_arrays is plain NumPy in the reference and
+  builds the neighbour table; compute_target_mesh runs on the shim)."""
+  out = {}
+  rng = np.random.default_rng(7)
+
+  # -- compose_maps_fast, both modes, fractional strides / starts ---------------
+  m1 = (rng.standard_normal((2, 2, 9, 11)) * 12).astype(np.float32)
+  m1[:, 0, 3, 4] = np.nan
+  m2 = (rng.standard_normal((2, 2, 13, 10)) * 6).astype(np.float32)
+  m2[0, 1, 5, 5] = np.nan
+  out['cmf_map1'], out['cmf_map2'] = m1, m2
+  out['cmf_args'] = np.array([3, 2, 1, 1, 4, 0], np.int64)  # start1 zyx, start2 zyx
+  for mode in ('nearest', 'constant'):
+    out[f'cmf_{mode}'] = np.asarray(mu.compose_maps_fast(
+        shim.asjax(m1), (3, 2, 1), (20, 25), shim.asjax(m2), (1, 4, 0), (16, 20),
+        mode=mode))
+  m13 = (rng.standard_normal((3, 4, 5, 6)) * 5).astype(np.float32)
+  m23 = (rng.standard_normal((3, 5, 6, 7)) * 3).astype(np.float32)
+  m13[:, 1, 2, 3] = np.nan
+  out['cmf3_map1'], out['cmf3_map2'] = m13, m23
+  for mode in ('nearest', 'constant'):
+    out[f'cmf3_{mode}'] = np.asarray(mu.compose_maps_fast(
+        shim.asjax(m13), (1, 0, 2), (4, 10, 10), shim.asjax(m23), (0, 1, 1), (4, 10, 10),
+        mode=mode))
+
+  # -- 2-d stitching: 3 x 2 tiles, mesh 12 x 14 nodes, stride 20 -----------------
+  def smooth(shape, amp):
+    return (ndi.gaussian_filter(rng.standard_normal(shape), (0,) * (len(shape) - 2) + (2, 2))
+            * amp).astype(np.float32)
+
+  nx_t, ny_t, stride = 3, 2, (20, 20)
+  tile_shape = (240, 280)
+  coords = [(tx, ty) for ty in range(ny_t) for tx in range(nx_t) if (tx, ty) != (2, 1)]
+  cx = np.full((2, ny_t, nx_t), np.nan)
+  cy = np.full((2, ny_t, nx_t), np.nan)
+  fine_x, fine_y, off_x, off_y = {}, {}, {}, {}
+  sizes_x = {(0, 0): (12, 4), (1, 0): (11, 3), (0, 1): (10, 4)}
+  sizes_y = {(0, 0): (3, 14), (1, 0): (4, 13), (2, 0): (3, 12)}
+  for k, (oy, ox) in sizes_x.items():
+    f = np.full((4, oy, ox), np.nan, np.float32)
+    f[:2] = smooth((2, oy, ox), 6.0)
+    f[2:] = 1.0
+    f[:, rng.integers(oy), rng.integers(ox)] = np.nan
+    fine_x[k] = f
+    cx[:, k[1], k[0]] = (260 + rng.integers(-5, 5), rng.integers(-30, 30))
+    off_x[k] = (int(rng.integers(-3, 3)), int(rng.integers(-3, 3)))
+  for k, (oy, ox) in sizes_y.items():
+    if (k[0], k[1] + 1) not in coords:
+      continue
+    f = np.full((4, oy, ox), np.nan, np.float32)
+    f[:2] = smooth((2, oy, ox), 6.0)
+    f[2:] = 1.0
+    fine_y[k] = f
+    cy[:, k[1], k[0]] = (rng.integers(-30, 30), 220 + rng.integers(-5, 5))
+    off_y[k] = (int(rng.integers(-3, 3)), int(rng.integers(-3, 3)))
+  coarse_mesh = np.zeros((2, ny_t, nx_t))
+  fx, fy, x, nbors, key_to_idx = se.aggregate_arrays(
+      (cx, fine_x, off_x), (cy, fine_y, off_y), coords, coarse_mesh, stride, tile_shape)
+  # inputs of aggregate_arrays, for the product's own aggregate_arrays
+  out['st2_coords'] = np.array(coords)
+  out['st2_cx'], out['st2_cy'] = cx, cy
+  for nm, fine, offs in (('x', fine_x, off_x), ('y', fine_y, off_y)):
+    for k, f in fine.items():
+      out[f'st2_fine{nm}_{k[0]}_{k[1]}'] = f
+      out[f'st2_off{nm}_{k[0]}_{k[1]}'] = np.array(offs[k])
+  out['st2_x0'] = x.astype(np.float32)
+  x = x + smooth(x.shape, 8.0)
+  x[:, 1, 4, 5] = np.nan
+  fx, fy, x = fx.astype(np.float32), fy.astype(np.float32), x.astype(np.float32)
+  out['st2_fx'], out['st2_fy'], out['st2_x'], out['st2_nbors'] = fx, fy, x, nbors
+  out['st2_stride'] = np.array(stride)
+  res = [np.asarray(se.compute_target_mesh(shim.asjax(nb), shim.asjax(x), shim.asjax(fx),
+                                           shim.asjax(fy), stride)) for nb in nbors]
+  out['st2_target'] = np.transpose(np.stack(res), [1, 0, 2, 3])
+
+  # -- the whole stitching relaxation of notebooks/em_stitching.ipynb:545-603 run by
+  # the reference's own mesh.relax_mesh with the notebook's prev_fn --------------
+  import functools as ft
+  import jax
+  import jax.numpy as jnp
+  mesh = shim.load_reference('mesh')
+  nb_j, fx_j, fy_j = shim.asjax(nbors), shim.asjax(fx), shim.asjax(fy)
+
+  def prev_fn(xx):
+    target_fn = ft.partial(se.compute_target_mesh, x=xx, fx=fx_j, fy=fy_j, stride=stride)
+    res = jax.vmap(target_fn)(nb_j)
+    return jnp.transpose(res, [1, 0, 2, 3])
+
+  cfg = dict(dt=0.001, gamma=0., k0=0.01, k=0.1, stride=stride, num_iters=12, max_iters=36,
+             stop_v_max=0.0, dt_max=100, prefer_orig_order=True, start_cap=0.1,
+             final_cap=10., remove_drift=True)
+  x_start = np.nan_to_num(x)  # the notebook starts from the (NaN-free) coarse mesh
+  out['st2_relax_cfg'] = np.array(repr(cfg))
+  out['st2_relax_x0'] = x_start
+  xr, ekin, t = mesh.relax_mesh(shim.asjax(x_start), None, mesh.IntegrationConfig(**cfg),
+                                prev_fn=prev_fn)
+  out['st2_relax_x'], out['st2_relax_ekin'], out['st2_relax_t'] = (
+      np.asarray(xr), np.asarray(ekin, dtype=np.float64), np.array(t))
+  cfg_nd = dict(cfg, remove_drift=False, fire=False, gamma=0.3, start_cap=10., final_cap=10.)
+  out['st2_relax_damped_cfg'] = np.array(repr(cfg_nd))
+  xr, ekin, t = mesh.relax_mesh(shim.asjax(x_start), None, mesh.IntegrationConfig(**cfg_nd),
+                                prev_fn=prev_fn)
+  out['st2_relax_damped_x'], out['st2_relax_damped_ekin'] = (
+      np.asarray(xr), np.asarray(ekin, dtype=np.float64))
+
+  # -- 3-d stitching (LICONN): 2 x 2 tiles, mesh 4 x 6 x 7 nodes, stride (8, 20, 20) --
+  stride3 = (8, 20, 20)
+  coords3 = [(0, 0), (1, 0), (0, 1), (1, 1)]
+  cx3 = np.full((3, 2, 2), np.nan)
+  cy3 = np.full((3, 2, 2), np.nan)
+  fine_x3, fine_y3, off_x3, off_y3 = {}, {}, {}, {}
+  for k, shp in {(0, 0): (4, 6, 3), (0, 1): (3, 5, 2)}.items():
+    f = np.full((5,) + shp, np.nan, np.float32)
+    f[:3] = (rng.standard_normal((3,) + shp) * 3).astype(np.float32)
+    fine_x3[k] = f
+    cx3[:, k[1], k[0]] = (120 + rng.integers(-3, 3), rng.integers(-15, 15), rng.integers(-6, 6))
+    off_x3[k] = tuple(int(v) for v in rng.integers(-2, 3, 3))
+  for k, shp in {(0, 0): (4, 2, 7), (1, 0): (3, 3, 6)}.items():
+    f = np.full((5,) + shp, np.nan, np.float32)
+    f[:3] = (rng.standard_normal((3,) + shp) * 3).astype(np.float32)
+    fine_y3[k] = f
+    cy3[:, k[1], k[0]] = (rng.integers(-15, 15), 100 + rng.integers(-3, 3), rng.integers(-6, 6))
+    off_y3[k] = tuple(int(v) for v in rng.integers(-2, 3, 3))
+  fx3, fy3, x3, nbors3, _ = se.aggregate_arrays(
+      (cx3, fine_x3, off_x3), (cy3, fine_y3, off_y3), coords3, np.zeros((3, 2, 2)), stride3,
+      (32, 120, 140))
+  x3 = x3 + (rng.standard_normal(x3.shape) * 4)
+  fx3, fy3, x3 = fx3.astype(np.float32), fy3.astype(np.float32), x3.astype(np.float32)
+  out['st3_fx'], out['st3_fy'], out['st3_x'], out['st3_nbors'] = fx3, fy3, x3, nbors3
+  out['st3_stride'] = np.array(stride3)
+  res = [np.asarray(se.compute_target_mesh(shim.asjax(nb), shim.asjax(x3), shim.asjax(fx3),
+                                           shim.asjax(fy3), stride3)) for nb in nbors3]
+  out['st3_target'] = np.transpose(np.stack(res), [1, 0, 2, 3, 4])
+  return out
+
+
 def main():
+  if 'stitch' in sys.argv[1:] or len(sys.argv) == 1:
+    mu = shim.load_reference('map_utils')
+    se = shim.load_reference('stitch_elastic')
+    np.savez_compressed(os.path.join(HERE, 'stitch_golden.npz'), **stitch_cases(mu, se))
+    print('stitch_golden.npz', os.path.getsize(os.path.join(HERE, 'stitch_golden.npz')) // 1024,
+          'KiB')
+    if len(sys.argv) > 1:
+      return
   mesh = shim.load_reference('mesh')
   ff = shim.load_reference('flow_field')
   np.savez_compressed(os.path.join(HERE, 'mesh_golden.npz'), **mesh_cases(mesh))

@@ -1,0 +1,108 @@
+"""Oracle of the stitching target-mesh path against the reference.
+
+* golden vectors: tests/golden/stitch_golden.npz, produced by the reference's own
+  map_utils.compose_maps_fast / stitch_elastic.{aggregate_arrays, compute_target_mesh}
+  (tests/golden/make_golden.py);
+* the reference's KAT tests/map_utils_test.py:266-300.
+CPU only.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import stitch_oracle as so
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'stitch_golden.npz')
+
+
+@pytest.fixture(scope='module')
+def g():
+  return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize('mode', ['nearest', 'constant'])
+def test_compose_maps_fast_golden(g, mode):
+  got = so.compose_maps_fast(g['cmf_map1'], (3, 2, 1), (20, 25), g['cmf_map2'], (1, 4, 0),
+                             (16, 20), mode=mode)
+  np.testing.assert_array_equal(got, g[f'cmf_{mode}'])
+  got = so.compose_maps_fast(g['cmf3_map1'], (1, 0, 2), (4, 10, 10), g['cmf3_map2'],
+                             (0, 1, 1), (4, 10, 10), mode=mode)
+  np.testing.assert_array_equal(got, g[f'cmf3_{mode}'])
+
+
+def test_compose_maps_fast_reference_kat():
+  # tests/map_utils_test.py:266-300 (BoundingBox starts are xyz; reversed = zyx)
+  coord_map = np.zeros([2, 1, 60, 60])
+  flow = np.zeros([2, 1, 50, 50])
+  flow[0, 0, :, 10:25] = -5
+  flow[0, 0, :, 25:40] = 65
+  flow[:, 0, :, 4] = np.nan
+  s1, s2 = (64, 58, 42), (64, 50, 40)
+  updated = so.compose_maps_fast(flow, s1, 40, coord_map, s2, 40)
+  np.testing.assert_array_equal(updated, flow)
+  coord_map[0, :, :, 7:] = -10
+  updated = so.compose_maps_fast(flow, s1, 40, coord_map, s2, 40)
+  flow[0, 0, :, 5:10] = -10
+  flow[0, 0, :, 10:25] = -15
+  flow[0, 0, :, 25:40] = 55
+  flow[0, 0, :, 40:] = -10
+  np.testing.assert_array_equal(updated, flow)
+
+
+def test_target_mesh_golden_2d(g):
+  got = so.target_mesh_all(g['st2_nbors'], g['st2_x'], g['st2_fx'], g['st2_fy'],
+                           tuple(int(v) for v in g['st2_stride']))
+  np.testing.assert_array_equal(got, g['st2_target'])
+  assert 0.2 < np.isfinite(got).mean() < 0.8  # targets exist in the overlaps only
+
+
+def test_target_mesh_golden_3d(g):
+  got = so.target_mesh_all(g['st3_nbors'], g['st3_x'], g['st3_fx'], g['st3_fy'],
+                           tuple(int(v) for v in g['st3_stride']))
+  np.testing.assert_array_equal(got, g['st3_target'])
+
+
+def _aggregate_inputs(g):
+  coords = [tuple(int(v) for v in c) for c in g['st2_coords']]
+  fine = {'x': {}, 'y': {}}
+  offs = {'x': {}, 'y': {}}
+  for key in g.files:
+    for nm in ('x', 'y'):
+      if key.startswith(f'st2_fine{nm}_'):
+        tx, ty = (int(v) for v in key.split('_')[2:])
+        fine[nm][tx, ty] = g[key]
+        offs[nm][tx, ty] = tuple(int(v) for v in g[f'st2_off{nm}_{tx}_{ty}'])
+  return coords, fine, offs
+
+
+def test_aggregate_arrays_matches_reference(g):
+  # host NumPy glue of the product (no GPU needed): same tables as the reference's.
+  from sofima_b200 import stitch_elastic
+  coords, fine, offs = _aggregate_inputs(g)
+  fx, fy, x, nbors, key_to_idx = stitch_elastic.aggregate_arrays(
+      (g['st2_cx'], fine['x'], offs['x']), (g['st2_cy'], fine['y'], offs['y']), coords,
+      np.zeros((2, 2, 3)), (20, 20), (240, 280))
+  np.testing.assert_array_equal(nbors, g['st2_nbors'])
+  np.testing.assert_array_equal(fx.astype(np.float32), g['st2_fx'])
+  np.testing.assert_array_equal(fy.astype(np.float32), g['st2_fy'])
+  np.testing.assert_array_equal(x, g['st2_x0'])
+  assert key_to_idx == {c: i for i, c in enumerate(coords)}
+
+
+@pytest.mark.parametrize('tag,atol', [('st2_relax', 2e-6), ('st2_relax_damped', 0.0)])
+def test_relaxation_with_stitching_prev_fn_golden(g, tag, atol):
+  # The whole notebooks/em_stitching.ipynb:545-603 solve, run by the reference's own
+  # mesh.relax_mesh + compute_target_mesh.  remove_drift takes fp32 means whose
+  # summation order is unspecified (oracle: fp64), hence 2e-6 there.
+  import ast
+  from oracle import mesh_oracle as mo
+  from sofima_b200.mesh import IntegrationConfig
+  stride = tuple(int(v) for v in g['st2_stride'])
+  prev_fn = lambda x: so.target_mesh_all(g['st2_nbors'], x, g['st2_fx'], g['st2_fy'], stride)
+  cfg = IntegrationConfig(**ast.literal_eval(str(g[f'{tag}_cfg'])))
+  x, e_kin, t = mo.relax_mesh(g['st2_relax_x0'], None, cfg, prev_fn=prev_fn)
+  assert t == 36
+  np.testing.assert_allclose(x, g[f'{tag}_x'], rtol=0, atol=atol)
+  np.testing.assert_allclose(e_kin, g[f'{tag}_ekin'], rtol=1e-6)
