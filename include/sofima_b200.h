@@ -77,6 +77,11 @@ enum {
 typedef struct {
   int32_t ncomp;
   int64_t nb, nz, ny, nx;
+  /* Number of batch dimensions folded into nb (3-d meshes only; 0 for [3, z, y, x]).
+   * It only matters for remove_drift: the reference averages over axes (1, 2, 3)
+   * literally (mesh.py:496-497), which for a [3, tiles, z, y, x] mesh is one mean per
+   * x column over (tiles, z, y). */
+  int32_t batch_rank;
 } sofima_mesh_shape;
 
 /* Replaces mesh.inplane_force / mesh.elastic_mesh_3d called on their own
@@ -129,24 +134,28 @@ typedef struct {
  * `prev_fn` closure of notebooks/em_stitching.ipynb:545-549.  All pointers are
  * device pointers. */
 typedef struct {
-  const float* fx;      /* [2, ntiles, fx_ny, fx_nx] flows between horizontal neighbours */
-  const float* fy;      /* [2, ntiles, fy_ny, fy_nx] flows between vertical neighbours */
-  const int32_t* nbors; /* [ntiles, 4, 8] NeighborInfo table (stitch_elastic.py:43-72) */
-  int64_t fx_ny, fx_nx, fy_ny, fy_nx;
-  double stride[2];     /* yx stride of the mesh / flow grids in pixels */
+  const float* fx;      /* [ndim, ntiles, (fz,) fy, fx] flows between horizontal neighbours */
+  const float* fy;      /* [ndim, ntiles, (fz,) fy, fx] flows between vertical neighbours */
+  const int32_t* nbors; /* [ntiles, 4, 8 (2-d) or 11 (3-d)] NeighborInfo table
+                           (stitch_elastic.py:43-72) */
+  int32_t ndim;         /* 2: tile meshes [2, n, y, x]; 3: [3, n, z, y, x] */
+  int64_t fx_shape[3];  /* zyx extent of one fx entry (2-d: [0] = 1) */
+  int64_t fy_shape[3];
+  double stride[3];     /* zyx stride of the mesh / flow grids in pixels (2-d: [0] unused) */
 } sofima_stitch_target;
 
-/* out[2, ntiles, ny, nx] = target mesh of every tile for the tile meshes
- * x[2, ntiles, ny, nx] (shape->nb = ntiles, shape->nz = 1). */
+/* out[ndim, ntiles, (nz,) ny, nx] = target mesh of every tile for the tile meshes x of
+ * the same shape (shape->nb = ntiles; 2-d: shape->nz = 1). */
 int sofima_stitch_target_mesh(sofima_ctx* ctx, const float* x,
                               const sofima_mesh_shape* shape,
                               const sofima_stitch_target* target, float* out);
 
 /* sofima_mesh_chunk for mesh.relax_mesh(x, None, config, prev_fn=...) with the
  * stitching prev_fn: `prev` is re-evaluated on the device from the advanced
- * positions inside every step (mesh.py:429-430), in-plane force only. */
-int sofima_mesh_chunk_stitch(sofima_ctx* ctx, float* x, float* v, float* a,
-                             const sofima_stitch_target* target,
+ * positions inside every step (mesh.py:429-430).  target->ndim must match the force
+ * kind (2: SOFIMA_FORCE_INPLANE, 3: SOFIMA_FORCE_MESH3D). */
+int sofima_mesh_chunk_stitch(sofima_ctx* ctx, int force_kind, float* x, float* v,
+                             float* a, const sofima_stitch_target* target,
                              const sofima_mesh_shape* shape,
                              const sofima_integration_config* cfg, float* dt,
                              float* alpha, float* cap, int32_t* n_pos,

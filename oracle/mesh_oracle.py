@@ -241,7 +241,10 @@ def velocity_verlet(x, v, prev, config, force_cap, fire_dt=None,
       cap = min(cap, F32(config.final_cap))
       v = v * F32(1.0 if pos else 0.0)
       if config.remove_drift:
-        axes = tuple(range(1, x.ndim))
+        # mesh.py:496-497 averages over axes (1, 2, 3) LITERALLY: all of (z, y, x) for
+        # [N, z, y, x] meshes, but only (batch, z, y) -- one mean per x column -- for
+        # the 5-d [3, tiles, z, y, x] meshes of 3-d stitching.
+        axes = (1, 2, 3)
         x = x - np.mean(x, axis=axes, keepdims=True, dtype=np.float64).astype(F32)
         v = v - np.mean(v, axis=axes, keepdims=True, dtype=np.float64).astype(F32)
       if trace is not None:

@@ -107,7 +107,7 @@ class IntegrationConfigPod(ctypes.Structure):
 class MeshShape(ctypes.Structure):
   _fields_ = [('ncomp', ctypes.c_int32), ('nb', ctypes.c_int64),
               ('nz', ctypes.c_int64), ('ny', ctypes.c_int64),
-              ('nx', ctypes.c_int64)]
+              ('nx', ctypes.c_int64), ('batch_rank', ctypes.c_int32)]
 
 
 class MeshState(ctypes.Structure):
@@ -121,10 +121,9 @@ class MeshState(ctypes.Structure):
 
 class StitchTargetPod(ctypes.Structure):
   _fields_ = [('fx', ctypes.c_void_p), ('fy', ctypes.c_void_p),
-              ('nbors', ctypes.c_void_p),
-              ('fx_ny', ctypes.c_int64), ('fx_nx', ctypes.c_int64),
-              ('fy_ny', ctypes.c_int64), ('fy_nx', ctypes.c_int64),
-              ('stride', ctypes.c_double * 2)]
+              ('nbors', ctypes.c_void_p), ('ndim', ctypes.c_int32),
+              ('fx_shape', ctypes.c_int64 * 3), ('fy_shape', ctypes.c_int64 * 3),
+              ('stride', ctypes.c_double * 3)]
 
 
 class XcorrParams(ctypes.Structure):
@@ -164,7 +163,7 @@ _PROTOS = {
         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
         ctypes.POINTER(ctypes.c_float)]),
     'sofima_mesh_chunk_stitch': (ctypes.c_int, [
-        _vp, _vp, _vp, _vp, ctypes.POINTER(StitchTargetPod), ctypes.POINTER(MeshShape),
+        _vp, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(StitchTargetPod), ctypes.POINTER(MeshShape),
         ctypes.POINTER(IntegrationConfigPod), ctypes.POINTER(ctypes.c_float),
         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),

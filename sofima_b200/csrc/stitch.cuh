@@ -238,3 +238,158 @@ __global__ void __launch_bounds__(kThreads) compose_maps_kernel(const ComposePar
 #pragma unroll
   for (int a = 3 - DIM; a < 3; ++a) q.out[(2 - a) * n + i] = acc[a] - ref1[a];
 }
+
+// ---------------------------------------------------------------------------------
+// 3-d tile meshes (LICONN in-plane stitching, x [3, tiles, z, y, x], neighbour rows of
+// 11 entries): same construction with a z window (stitch_elastic.py:505-516, :549-556)
+// and trilinear sampling (8 corners, z slowest; weights (wz * wy) * wx).
+//   SRC 0: component-major positions as stored; SRC 2: advanced by the pending step
+//   (the arithmetic of mesh3d_kernel's `advance`).
+// ---------------------------------------------------------------------------------
+struct StitchParams3 {
+  const float* fx;   // [3][nt][fx_n zyx]
+  const float* fy;
+  const int* nbors;  // [nt][4][11]
+  int nt;
+  int m[3];          // mesh zyx
+  int fxn[3], fyn[3];
+  float stride[3];   // zyx
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(kThreads)
+stitch_target3d_kernel(const Params p, const StitchParams3 q, int fire, float* out) {
+  const int t = blockIdx.y;
+  const long long tile_nodes = (long long)q.m[0] * q.m[1] * q.m[2];
+  const long long node = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (node >= tile_nodes) return;
+  const int px = (int)(node % q.m[2]);
+  const int py = (int)((node / q.m[2]) % q.m[1]);
+  const int pz = (int)(node / ((long long)q.m[2] * q.m[1]));
+  const int ppos[3] = {pz, py, px};
+  const float qnan = __int_as_float(0x7fc00000);
+  const long long cs = p.comp_stride;
+
+  float dt = 0.f, hdt2 = 0.f, gate = 1.f;
+  float mx[3] = {0.f, 0.f, 0.f}, mv[3] = {0.f, 0.f, 0.f};
+  bool lazy = false, drift = false;
+  if (SRC == 2) {
+    if (fire) {
+      const State S = *p.state;
+      dt = S.dt;
+      gate = S.gate;
+      hdt2 = 0.5f * (dt * dt);
+      lazy = true;
+      drift = p.drift == 1;
+      if (drift)
+        for (int c = 0; c < 3; ++c) { mx[c] = S.mean_x[c]; mv[c] = S.mean_v[c]; }
+    } else {
+      dt = p.c_dt;
+      hdt2 = p.c_hdt2;
+    }
+  }
+  const bool coldrift = lazy && p.drift == 2;  // per-column means, see Params::col_mean
+  auto position = [&](long long o, int gx, int c) -> float {
+    float xc = __ldg(p.xi + o + c * cs);
+    if (SRC == 2) {
+      float vc = __ldg(p.vi + o + c * cs);
+      const float ac = __ldg(p.ai + o + c * cs);
+      if (lazy) {
+        vc = vc * gate;
+        if (coldrift) {
+          xc = xc - __ldcg(&p.col_mean[c * q.m[2] + gx]);
+          vc = vc - __ldcg(&p.col_mean[(3 + c) * q.m[2] + gx]);
+        } else if (drift) {
+          xc = xc - mx[c];
+          vc = vc - mv[c];
+        }
+      }
+      xc = xc + (dt * vc + hdt2 * ac);
+    }
+    return xc;
+  };
+
+  float cur[3] = {qnan, qnan, qnan};  // xyz components
+  for (int k = 0; k < 4; ++k) {
+    const int* nd = q.nbors + ((long long)t * 4 + k) * 11;
+    const int nbor = nd[0];
+    if (nbor == -1) continue;
+    const int fidx = nd[1];
+    const int mult = (nbor == fidx) ? 1 : -1;
+    const bool horiz = nd[7] == 0;
+    const int d = horiz ? 0 : 1;
+    const float* F = horiz ? q.fx : q.fy;
+    const int* fn = horiz ? q.fxn : q.fyn;
+    const int flow_overlap = nd[4], flow_ortho = nd[3], off_ortho = nd[2];
+    const int off_z = nd[8], flow_z = nd[9];
+    const int par_size = horiz ? q.m[2] : q.m[1];
+    const int ortho_size = horiz ? q.m[1] : q.m[2];
+    const int tg_par = (mult == 1) ? 0 : par_size - flow_overlap;
+    const int tg_ortho = ((mult == 1 && off_ortho < 0) || (mult == -1 && off_ortho > 0))
+                             ? ortho_size - flow_ortho : 0;
+    const int tg_z = ((mult == 1 && off_z < 0) || (mult == -1 && off_z > 0)) ? q.m[0] - flow_z : 0;
+    int tg[3] = {tg_z, tg_par * d + (1 - d) * tg_ortho, tg_par * (1 - d) + d * tg_ortho};
+    int idx[3];
+    bool inside = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ext = q.m[a] + max(q.fyn[a], q.fxn[a]);
+      tg[a] = min(max(tg[a], 0), ext - fn[a]);
+      idx[a] = ppos[a] - tg[a];
+      inside = inside && idx[a] >= 0 && idx[a] < fn[a];
+    }
+    if (!inside) continue;
+    const int st_par = (mult == 1) ? par_size - flow_overlap : 0;
+    const int st_ortho = ((mult == 1 && off_ortho > 0) || (mult == -1 && off_ortho < 0))
+                             ? ortho_size - flow_ortho : 0;
+    const int st_z = ((mult == 1 && off_z > 0) || (mult == -1 && off_z < 0)) ? q.m[0] - flow_z : 0;
+    const int st[3] = {st_z, st_ortho * (1 - d) + d * st_par, st_ortho * d + (1 - d) * st_par};
+    const long long fvol = (long long)fn[0] * fn[1] * fn[2];
+    const long long fo = (long long)fidx * fvol + ((long long)idx[0] * fn[1] + idx[1]) * fn[2] + idx[2];
+    const long long fcs = (long long)q.nt * fvol;
+    int org[3];
+    float ref1[3], coord[3];
+    bool bad = false;
+    int i0[3];
+    float w[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      org[a] = min(st[a], 0);
+      ref1[a] = (float)(idx[a] + (st[a] - org[a])) * q.stride[a];
+      const float f = (float)mult * __ldg(F + fo + (2 - a) * fcs);  // component 2 - a
+      coord[a] = (ref1[a] + f) / q.stride[a];
+      const float lower = floorf(coord[a]);
+      if (!(fabsf(lower) < 1.0e9f)) bad = true;
+      w[a][1] = coord[a] - lower;
+      w[a][0] = 1.0f - w[a][1];
+      i0[a] = (int)lower;
+    }
+    if (bad) continue;  // NaN / far out of range: the update is NaN in all components
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int cz = i0[0] + ((c >> 2) & 1), cy = i0[1] + ((c >> 1) & 1), cx = i0[2] + (c & 1);
+      const float wt = (w[0][(c >> 2) & 1] * w[1][(c >> 1) & 1]) * w[2][c & 1];
+      const bool valid = cz >= 0 && cz < q.m[0] && cy >= 0 && cy < q.m[1] && cx >= 0 && cx < q.m[2];
+      const int cpos[3] = {cz, cy, cx};
+      const long long o = (long long)nbor * tile_nodes + ((long long)cz * q.m[1] + cy) * q.m[2] + cx;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float v = qnan;
+        if (valid) v = position(o, cx, 2 - a) + (float)(cpos[a] - org[a]) * q.stride[a];
+        const float term = wt * v;
+        acc[a] = (c == 0) ? term : acc[a] + term;
+      }
+    }
+    const int fine[3] = {nd[10], nd[6], nd[5]};  // zyx
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float u = acc[a] - ref1[a];
+      u = u + (float)(mult * fine[a]);
+      if (u == u) cur[2 - a] = u;
+    }
+  }
+  const long long o = (long long)t * tile_nodes + node;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[o + c * (long long)q.nt * tile_nodes] = cur[c];
+}

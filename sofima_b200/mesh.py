@@ -125,12 +125,12 @@ def _shape_pod(shape: Sequence[int], kind: int) -> _native.MeshShape:
   if kind == _INPLANE:
     if len(shape) != 4 or shape[0] != 2:
       raise ValueError(f'expected a [2, z, y, x] mesh, got shape {tuple(shape)}')
-    return _native.MeshShape(2, shape[1], 1, shape[2], shape[3])
+    return _native.MeshShape(2, shape[1], 1, shape[2], shape[3], 0)
   if len(shape) < 4 or shape[0] != 3:
     raise ValueError(
         f'expected a [3, [batch..], z, y, x] mesh, got shape {tuple(shape)}')
   nb = int(np.prod(shape[1:-3])) if len(shape) > 4 else 1
-  return _native.MeshShape(3, nb, shape[-3], shape[-2], shape[-1])
+  return _native.MeshShape(3, nb, shape[-3], shape[-2], shape[-1], len(shape) - 4)
 
 
 def _stride3(stride, kind: int):
@@ -272,7 +272,7 @@ class _Chunk:
     self.ctx.bind_stream()
     if self.target is not None:
       rc = _native.lib().sofima_mesh_chunk_stitch(
-          self.ctx.handle, self.x.data_ptr(), self.v.data_ptr(), self.a.data_ptr(),
+          self.ctx.handle, self.kind, self.x.data_ptr(), self.v.data_ptr(), self.a.data_ptr(),
           ctypes.byref(self.target), ctypes.byref(self.shape), ctypes.byref(self.pod),
           ctypes.byref(c_dt), ctypes.byref(c_alpha), ctypes.byref(c_cap),
           ctypes.byref(n_pos), ctypes.byref(e_kin), ctypes.byref(v_max))
@@ -300,10 +300,10 @@ def _stitch_target(prev_fn, kind: int, x_shape, ctx):
         'sofima_b200.stitch_elastic.target_mesh_fn(nbors, fx, fy, stride) (the '
         'stitching prev_fn of stitch_elastic.compute_target_mesh); arbitrary Python '
         f'callables such as {prev_fn!r} cannot be traced into it.')
-  if kind != _INPLANE:
-    raise NotImplementedError(
-        'prev_fn with the 3-d mesh force is not part of the CUDA backend yet.')
-  return describe(x_shape, ctx)
+  pod = describe(x_shape, ctx)
+  if pod.ndim != (2 if kind == _INPLANE else 3):
+    raise ValueError('prev_fn and mesh_force disagree on the mesh dimensionality')
+  return pod
 
 
 def velocity_verlet(x, v, prev, config: IntegrationConfig, force_cap: float,

@@ -124,10 +124,8 @@ class StitchTarget:
     if nbors.ndim != 3 or nbors.shape[1] != 4:
       raise ValueError(f'nbors must be [n, 4, 8 or 11], got {nbors.shape}')
     self.dim = len(stride)
-    if self.dim != 2 or nbors.shape[2] != 8:
-      raise NotImplementedError(
-          'The CUDA stitching target is built for 2-d tile meshes ([n, 4, 8] neighbour '
-          'tables); 3-d (LICONN) stitching targets are not part of the backend yet.')
+    if self.dim not in (2, 3) or nbors.shape[2] != (8 if self.dim == 2 else 11):
+      raise ValueError('stride must be [z]yx and nbors [n, 4, 8] (2-d) or [n, 4, 11] (3-d)')
     n = nbors.shape[0]
     if np.any(nbors[:, :, 0] < -1) or np.any(nbors[:, :, 0] >= n) or np.any(
         (nbors[:, :, 0] >= 0) & ((nbors[:, :, 1] < 0) | (nbors[:, :, 1] >= n))):
@@ -137,8 +135,9 @@ class StitchTarget:
     self._nbors_host = np.ascontiguousarray(nbors, dtype=np.int32)
     self._fx_in, self._fy_in = fx, fy
     for f in (fx, fy):
-      if len(f.shape) != 4 or f.shape[0] != 2 or f.shape[1] != n:
-        raise ValueError(f'flow arrays must be [2, {n}, y, x], got {tuple(f.shape)}')
+      if len(f.shape) != self.dim + 2 or f.shape[0] != self.dim or f.shape[1] != n:
+        raise ValueError(
+            f'flow arrays must be [{self.dim}, {n}, [z,] y, x], got {tuple(f.shape)}')
     self._dev = {}  # device index -> (fx, fy, nbors) tensors
 
   def _arrays(self, ctx):
@@ -152,14 +151,18 @@ class StitchTarget:
     return arrs
 
   def _sofima_device_target(self, x_shape, ctx) -> _native.StitchTargetPod:
-    if len(x_shape) != 4 or x_shape[0] != 2 or x_shape[1] != self.ntiles:
-      raise ValueError(f'x must be [2, {self.ntiles}, y, x], got {tuple(x_shape)}')
+    d = self.dim
+    if len(x_shape) != d + 2 or x_shape[0] != d or x_shape[1] != self.ntiles:
+      raise ValueError(f'x must be [{d}, {self.ntiles}, [z,] y, x], got {tuple(x_shape)}')
     fx, fy, nb = self._arrays(ctx)
     pod = _native.StitchTargetPod()
     pod.fx, pod.fy, pod.nbors = fx.data_ptr(), fy.data_ptr(), nb.data_ptr()
-    pod.fx_ny, pod.fx_nx = fx.shape[2], fx.shape[3]
-    pod.fy_ny, pod.fy_nx = fy.shape[2], fy.shape[3]
-    pod.stride[0], pod.stride[1] = self.stride
+    pod.ndim = d
+    for a in range(3):
+      j = a - (3 - d)  # index into the [z]yx tuples
+      pod.fx_shape[a] = fx.shape[2 + j] if j >= 0 else 1
+      pod.fy_shape[a] = fy.shape[2 + j] if j >= 0 else 1
+      pod.stride[a] = self.stride[j] if j >= 0 else 0.0
     return pod
 
   def __call__(self, x):
@@ -167,7 +170,10 @@ class StitchTarget:
     ctx = _native.Context.get(dev)
     xd = _mesh._to_device(x, ctx, copy=False)
     pod = self._sofima_device_target(tuple(xd.shape), ctx)
-    shape = _native.MeshShape(2, xd.shape[1], 1, xd.shape[2], xd.shape[3])
+    if self.dim == 2:
+      shape = _native.MeshShape(2, xd.shape[1], 1, xd.shape[2], xd.shape[3], 0)
+    else:
+      shape = _native.MeshShape(3, xd.shape[1], xd.shape[2], xd.shape[3], xd.shape[4], 1)
     out = _mesh._torch().empty_like(xd)
     ctx.bind_stream()
     rc = _native.lib().sofima_stitch_target_mesh(
@@ -185,14 +191,14 @@ def compute_target_mesh(nbor_data, x, fx, fy, stride: Sequence[float] = (20, 20)
   """Target mesh of ONE tile (stitch_elastic.py:624-676).
 
   Args:
-    nbor_data: [4, 8] neighbour info of the tile; -1 in the nbor and flow indices
-      marks missing entries
-    x: [2, n, y, x] node positions of all tiles
-    fx, fy: [2, n, y, x] flows between horizontal / vertical neighbours
-    stride: yx stride of flow and mesh data
+    nbor_data: [4, 8 or 11] neighbour info of the tile; -1 in the nbor and flow
+      indices marks missing entries
+    x: [2 or 3, n, [z,] y, x] node positions of all tiles
+    fx, fy: [2 or 3, n, [z,] y, x] flows between horizontal / vertical neighbours
+    stride: [z]yx stride of flow and mesh data
 
   Returns:
-    [2, y, x] target positions (NaN where no neighbour provides one)
+    [2 or 3, [z,] y, x] target positions (NaN where no neighbour provides one)
   """
   nbor_data = np.asarray(nbor_data)
   n = x.shape[1]

@@ -372,6 +372,26 @@ def stitch_cases(mu, se):
   res = [np.asarray(se.compute_target_mesh(shim.asjax(nb), shim.asjax(x3), shim.asjax(fx3),
                                            shim.asjax(fy3), stride3)) for nb in nbors3]
   out['st3_target'] = np.transpose(np.stack(res), [1, 0, 2, 3, 4])
+
+  # notebooks/liconn_inplane_stitching.ipynb:763-783: 3-d relaxation with prev_fn.
+  nb3_j, fx3_j, fy3_j = shim.asjax(nbors3), shim.asjax(fx3), shim.asjax(fy3)
+
+  def prev_fn3(xx):
+    target_fn = ft.partial(se.compute_target_mesh, x=xx, fx=fx3_j, fy=fy3_j, stride=stride3)
+    res = jax.vmap(target_fn)(nb3_j)
+    return jnp.transpose(res, [1, 0, 2, 3, 4])
+
+  # mesh.elastic_mesh_3d takes the stride in xyz order; the target in zyx.
+  cfg3 = dict(dt=0.001, gamma=0., k0=0.01, k=0.1, stride=stride3[::-1], num_iters=8,
+              max_iters=24, stop_v_max=0.0, dt_max=100, prefer_orig_order=False,
+              start_cap=0.1, final_cap=10., remove_drift=True)
+  out['st3_relax_cfg'] = np.array(repr(cfg3))
+  for tag, kw in (('st3_relax', {}), ('st3_relax_nodrift', dict(remove_drift=False))):
+    c = dict(cfg3, **kw)
+    out[f'{tag}_cfg'] = np.array(repr(c))
+    xr, ekin, t = mesh.relax_mesh(shim.asjax(x3), None, mesh.IntegrationConfig(**c),
+                                  prev_fn=prev_fn3, mesh_force=mesh.elastic_mesh_3d)
+    out[f'{tag}_x'], out[f'{tag}_ekin'] = np.asarray(xr), np.asarray(ekin, dtype=np.float64)
   return out
 
 

@@ -106,3 +106,21 @@ def test_relaxation_with_stitching_prev_fn_golden(g, tag, atol):
   assert t == 36
   np.testing.assert_allclose(x, g[f'{tag}_x'], rtol=0, atol=atol)
   np.testing.assert_allclose(e_kin, g[f'{tag}_ekin'], rtol=1e-6)
+
+
+@pytest.mark.parametrize('tag,atol', [('st3_relax', 2e-6), ('st3_relax_nodrift', 0.0)])
+def test_relaxation_3d_with_stitching_prev_fn_golden(g, tag, atol):
+  # notebooks/liconn_inplane_stitching.ipynb:763-783 run by the reference's own code:
+  # [3, tiles, z, y, x] meshes, elastic_mesh_3d.  With remove_drift the reference's
+  # mean over axes (1, 2, 3) is one mean per x column (mesh.py:496-497).
+  import ast
+  from oracle import mesh_oracle as mo
+  from sofima_b200.mesh import IntegrationConfig
+  stride = tuple(int(v) for v in g['st3_stride'])
+  prev_fn = lambda x: so.target_mesh_all(g['st3_nbors'], x, g['st3_fx'], g['st3_fy'], stride)
+  cfg = IntegrationConfig(**ast.literal_eval(str(g[f'{tag}_cfg'])))
+  x, e_kin, t = mo.relax_mesh(g['st3_x'], None, cfg, prev_fn=prev_fn,
+                              mesh_force=mo.elastic_mesh_3d)
+  assert t == 24
+  np.testing.assert_allclose(x, g[f'{tag}_x'], rtol=0, atol=atol)
+  np.testing.assert_allclose(e_kin, g[f'{tag}_ekin'], rtol=1e-6)

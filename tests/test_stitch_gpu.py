@@ -106,6 +106,33 @@ def test_target_mesh_golden(mods, g):
     np.testing.assert_array_equal(one, g['st2_target'][:, i])
 
 
+def test_target_mesh_golden_3d(mods, g):
+  stitch_elastic = mods[2]
+  stride = tuple(int(v) for v in g['st3_stride'])
+  fn = stitch_elastic.target_mesh_fn(g['st3_nbors'], g['st3_fx'], g['st3_fy'], stride)
+  np.testing.assert_array_equal(fn(g['st3_x']), g['st3_target'])
+  one = stitch_elastic.compute_target_mesh(g['st3_nbors'][2], g['st3_x'], g['st3_fx'],
+                                           g['st3_fy'], stride)
+  np.testing.assert_array_equal(one, g['st3_target'][:, 2])
+
+
+@pytest.mark.parametrize('tag,atol', [('st3_relax', 1e-5), ('st3_relax_nodrift', 1e-6)])
+def test_relax_mesh_3d_with_prev_fn_golden(mods, g, tag, atol):
+  """notebooks/liconn_inplane_stitching.ipynb:763-783 against the reference's own
+  trajectory (remove_drift there is one mean per x column, mesh.py:496-497)."""
+  _, mesh, stitch_elastic = mods
+  stride = tuple(int(v) for v in g['st3_stride'])
+  prev_fn = stitch_elastic.target_mesh_fn(g['st3_nbors'], g['st3_fx'], g['st3_fy'], stride)
+  cfg = mesh.IntegrationConfig(**ast.literal_eval(str(g[f'{tag}_cfg'])))
+  x, e_kin, t = mesh.relax_mesh(g['st3_x'], None, cfg, prev_fn=prev_fn,
+                                mesh_force=mesh.elastic_mesh_3d)
+  assert t == 24
+  np.testing.assert_allclose(x, g[f'{tag}_x'], rtol=0, atol=atol)
+  np.testing.assert_allclose(e_kin, g[f'{tag}_ekin'], rtol=1e-5)
+  with pytest.raises(ValueError):  # 2-d force with a 3-d target
+    mesh.relax_mesh(g['st3_x'][:2, :, 0], None, cfg, prev_fn=prev_fn)
+
+
 def _big_case(seed=3, nt_x=4, nt_y=3, mesh_shape=(51, 48), stride=(40.0, 40.0)):
   """A 4 x 3 tile grid with jittered overlaps, built through aggregate_arrays."""
   from sofima_b200 import stitch_elastic
