@@ -252,6 +252,56 @@ patch_mean_kernel(Problem P, MeanPartial* parts) {
   }
 }
 
+// uint8 images without masks (every BASELINE flow configuration): the patch rows are
+// read as aligned 32-bit words and summed four pixels at a time with dp4a; bytes
+// outside [x0, x0 + pw) are masked off.  Same grid, same exact integer partial sums.
+__global__ void __launch_bounds__(kThreads)
+patch_sum_u8_kernel(Problem P, MeanPartial* parts) {
+  // grid = (pair, image); warp g sums row group g (kMeanGroups == warps per block).
+  static_assert(kMeanGroups == kThreads / 32, "one warp per row group");
+  const int which = blockIdx.y;
+  const long long b = P.b0 + blockIdx.x;
+  const Image& I = P.img[which];
+  const int y0 = clamp_start(P.starts[which][b * 2 + 0], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[which][b * 2 + 1], I.pw, I.w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows_per = ceil_div(I.ph, kMeanGroups);
+  const int ya = warp * rows_per, yb = min(I.ph, ya + rows_per);
+  const uint8_t* img = static_cast<const uint8_t*>(I.data);
+  const uint8_t* img_end = img + (long long)I.h * I.w;
+  unsigned int isum = 0;
+#pragma unroll 4
+  for (int y = ya; y < yb; ++y) {
+    const uint8_t* src = img + (long long)(y0 + y) * I.w + x0;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
+    const uint8_t* wbase = src - mis;
+    const int nwords = (mis + I.pw + 3) >> 2;
+    for (int i = lane; i < nwords; i += 32) {
+      const uint8_t* wp = wbase + 4 * i;
+      const int first = max(mis - 4 * i, 0);            // first valid byte of the word
+      const int last = min(mis + I.pw - 4 * i, 4);      // one past the last valid byte
+      if (wp >= img && wp + 4 <= img_end) {
+        unsigned int wv = __ldg(reinterpret_cast<const unsigned int*>(wp));
+        unsigned int m = 0xffffffffu;
+        if (first > 0) m &= 0xffffffffu << (8 * first);
+        if (last < 4) m &= (1u << (8 * last)) - 1u;
+        isum = __dp4a(wv & m, 0x01010101u, isum);
+      } else {  // the word straddles the ends of the image buffer
+        for (int j = first; j < last; ++j) isum += wp[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+  if (lane == 0) {
+    MeanPartial mp;
+    mp.sum = (double)isum;
+    mp.count = (yb > ya ? yb - ya : 0) * I.pw;
+    mp.pad = 0;
+    parts[(b * 2 + which) * kMeanGroups + warp] = mp;
+  }
+}
+
 // fp32 sum / fp32 count, as jnp.mean / jnp.nanmean (0 / 0 -> NaN).
 __device__ __forceinline__ float patch_mean(const Problem& P, long long b, int which) {
   if (P.has_mean) return P.mean;
@@ -1009,8 +1059,12 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       P.b0 = b0;
       P.nb = (int)((B - b0 < 65535) ? (B - b0) : 65535);
       LaunchTimer timer(ctx, "flow_mean");
-      patch_mean_kernel<<<dim3(P.nb, 2, kMeanGroups), kThreads, 0, ctx->stream>>>(
-          P, (MeanPartial*)means);
+      if (P.dtype == SOFIMA_U8 && !P.img[0].mask && !P.img[1].mask)
+        patch_sum_u8_kernel<<<dim3(P.nb, 2), kThreads, 0, ctx->stream>>>(
+            P, (MeanPartial*)means);
+      else
+        patch_mean_kernel<<<dim3(P.nb, 2, kMeanGroups), kThreads, 0, ctx->stream>>>(
+            P, (MeanPartial*)means);
       SOFIMA_CHECK_LAUNCH(ctx);
     }
   }

@@ -30,6 +30,12 @@ struct FastDims {
   static constexpr int L = kN1 * N2;
   static constexpr int N2P = N2 | 1;           // odd pitch: conflict-free exchange
   static constexpr int EX = kN1 * N2P + 2;     // float2 per exchange line (== 2 mod 16)
+  // Row kernels map threads transform-major (groups of N2 consecutive threads): the
+  // lines of consecutive transforms must continue the bank sequence, i.e. the line
+  // pitch is == N2 (mod 16) in float2 units ...
+  static constexpr int EXR = kN1 * N2P + ((N2 - kN1 * N2P) % 16 + 16) % 16;
+  // ... and two staged pixel rows (floats) advance the banks by N2 (mod 32).
+  static constexpr int PXP = L + (N2 / 2) % 16;
   static constexpr int LP = L + 2;             // padded spectrum line (== 2 mod 16)
   static constexpr int G = N2 > kN1 ? N2 : kN1;  // threads per transform
 };
@@ -47,10 +53,10 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
   constexpr int L = D::L;
   constexpr int NT = TR * D::G;
   constexpr int NKX = L / 2 + 1;
-  __shared__ float2 ex[TR * D::EX];
-  __shared__ float2 xs[TR * L];   // first the staged pixel rows (as float), then X
+  __shared__ float2 ex[TR * D::EXR];
+  __shared__ float2 xs[TR * D::PXP];   // first the staged pixel rows (as float), then X
   __shared__ float2 tw_s[L];
-  float* px = reinterpret_cast<float*>(xs);  // [2 TR][L]
+  float* px = reinterpret_cast<float*>(xs);  // [2 TR][PXP]
   const Slot sl = P.slot[blockIdx.y];
   const Image& I = P.img[sl.src];
   const long long b = P.b0 + blockIdx.z;
@@ -76,7 +82,7 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < 2 * TR; r += NT / 32) {
       const int y = 2 * rp0 + r;
-      float* dst = px + r * L;
+      float* dst = px + r * D::PXP;
       if (y >= nrows) {
         for (int x = lane; x < pw; x += 32) dst[x] = 0.f;
         continue;
@@ -103,8 +109,8 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
 
   if (threadIdx.x < TR * N2) {  // pass 1: thread (f, n2)
     const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
-    const float* r0 = px + (2 * f) * L;
-    const float* r1 = r0 + L;
+    const float* r0 = px + (2 * f) * D::PXP;
+    const float* r1 = r0 + D::PXP;
     float2 a[kN1];
 #pragma unroll
     for (int n1 = 0; n1 < kN1; ++n1) {
@@ -118,14 +124,14 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
     Dft<kN1>::run(a);
 #pragma unroll
     for (int k1 = 0; k1 < kN1; ++k1)
-      ex[f * D::EX + k1 * D::N2P + n2] = cmul(a[k1], tw_s[n2 * k1]);
+      ex[f * D::EXR + k1 * D::N2P + n2] = cmul(a[k1], tw_s[n2 * k1]);
   }
   __syncthreads();
   if (threadIdx.x < TR * kN1) {  // pass 2: thread (f, k1)
     const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
     float2 bq[N2];
 #pragma unroll
-    for (int n2 = 0; n2 < N2; ++n2) bq[n2] = ex[f * D::EX + k1 * D::N2P + n2];
+    for (int n2 = 0; n2 < N2; ++n2) bq[n2] = ex[f * D::EXR + k1 * D::N2P + n2];
     Dft<N2>::run(bq);
 #pragma unroll
     for (int k2 = 0; k2 < N2; ++k2) xs[f * L + k1 + kN1 * k2] = bq[k2];
@@ -245,7 +251,7 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
               int* nanflag, float* __restrict__ bandmax) {
   using D = FastDims<N2>;
   constexpr int L = D::L;
-  __shared__ float2 ex[TR * D::EX];
+  __shared__ float2 ex[TR * D::EXR];
   __shared__ float2 tw_s[L];
   constexpr int NT = TR * D::G;
   __shared__ unsigned long long kred[(NT + 31) / 32];
@@ -278,7 +284,7 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
     Dft<N2>::run(bq);
 #pragma unroll
     for (int n2 = 0; n2 < N2; ++n2)
-      ex[f * D::EX + k1 * D::N2P + n2] = cmul(bq[n2], tw_s[k1 * n2]);
+      ex[f * D::EXR + k1 * D::N2P + n2] = cmul(bq[n2], tw_s[k1 * n2]);
   }
   __syncthreads();
   unsigned long long best = 0;
@@ -288,7 +294,7 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
     const int y = 2 * (rp0 + f);
     float2 a[kN1];
 #pragma unroll
-    for (int k1 = 0; k1 < kN1; ++k1) a[k1] = ex[f * D::EX + k1 * D::N2P + n2];
+    for (int k1 = 0; k1 < kN1; ++k1) a[k1] = ex[f * D::EXR + k1 * D::N2P + n2];
     Dft<kN1>::run(a);
     if (y < P.sy) {
       float* out = images + (size_t)(P.b0 + blockIdx.z) * P.sy * P.sx;
