@@ -64,6 +64,14 @@ except ImportError:
       e = self.end + (0 if end is None else np.asarray(end))
       return BoundingBox(start=s, end=e)
 
+    def intersection(self, other: 'BoundingBox'):
+      """Overlap of two boxes, or None if they do not intersect."""
+      start = np.maximum(self.start, other.start)
+      end = np.minimum(self.end, other.end)
+      if np.any(end <= start):
+        return None
+      return BoundingBox(start=start, end=end)
+
     def translate(self, offset) -> 'BoundingBox':
       return BoundingBox(start=self.start + np.asarray(offset), size=self.size)
 

@@ -2,8 +2,10 @@
 
 The reference wraps TensorStore `virtual_chunked` views (`OptimFlow` :131,
 `MeshRelaxFlowFilter` :108).  TensorStore and gin are not available in this image,
-so this module provides the two chunk functions those decorators apply -- the part
-that reaches the hot path -- with the reference's argument conventions; the
+so this module provides the chunk functions those decorators apply (`optim_flow`,
+`mesh_relax_flow` reach the hot path; `clean_flow`, `reconcile_flow` are the host
+filters of `CleanFlowFilter` :47 / `ReconcileFlowFilter` :358) with the reference's
+argument conventions; the
 TensorStore wrappers raise a clear ImportError when constructed without it.
 """
 
@@ -14,7 +16,22 @@ from typing import Sequence
 import numpy as np
 
 from .. import flow_field
+from .. import flow_utils
 from .. import mesh
+
+
+def clean_flow(flow: np.ndarray, **filter_args) -> np.ndarray:
+  """Chunk function of `CleanFlowFilter` (decorators/flow.py:38-43): [dim + 2, ...]
+  flow with singleton non-spatial axes -> [dim, ...] cleaned vectors."""
+  final_shape = list(flow.shape)
+  final_shape[0] -= 2
+  return flow_utils.clean_flow(flow.squeeze(), dim=flow.shape[0] - 2,
+                               **filter_args).reshape(final_shape)
+
+
+def reconcile_flow(flow: np.ndarray, **filter_args) -> np.ndarray:
+  """Chunk function of `ReconcileFlowFilter` (decorators/flow.py:349-354)."""
+  return flow_utils.reconcile_flows([flow.squeeze()], **filter_args).reshape(flow.shape)
 
 
 def mesh_relax_flow(flow: np.ndarray, **filter_args) -> np.ndarray:
@@ -73,3 +90,11 @@ class MeshRelaxFlowFilter(_NeedsTensorStore):
 
 class OptimFlow(_NeedsTensorStore):
   """decorators/flow.py:131-355."""
+
+
+class CleanFlowFilter(_NeedsTensorStore):
+  """decorators/flow.py:47-86."""
+
+
+class ReconcileFlowFilter(_NeedsTensorStore):
+  """decorators/flow.py:358-369."""
