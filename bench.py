@@ -66,6 +66,45 @@ def _peaks():
 # ----------------------------------------------------------------------------------
 # synthetic data
 # ----------------------------------------------------------------------------------
+def synth_stitch(nt_x, nt_y, mesh_shape, stride=(40.0, 40.0), seed=1):
+  """Flow fields, coarse offsets and the neighbour table of an nt_x x nt_y tile grid
+  with ~10 % overlap (3-5 flow columns / rows per seam), through aggregate_arrays."""
+  import scipy.ndimage as ndi
+  from sofima_b200 import stitch_elastic
+  rng = np.random.default_rng(seed)
+  my, mx = mesh_shape
+  coords = [(tx, ty) for ty in range(nt_y) for tx in range(nt_x)]
+  cx = np.full((2, nt_y, nt_x), np.nan)
+  cy = np.full((2, nt_y, nt_x), np.nan)
+  fine_x, fine_y, off_x, off_y = {}, {}, {}, {}
+
+  def smooth(shape, amp):
+    return (ndi.gaussian_filter(rng.standard_normal(shape), (0, 2, 2)) * amp).astype(np.float32)
+
+  for tx, ty in coords:
+    if tx + 1 < nt_x:
+      oy, ox = my - int(rng.integers(0, 3)), int(rng.integers(3, 6))
+      f = np.full((4, oy, ox), 1.0, np.float32)
+      f[:2] = smooth((2, oy, ox), 5.0)
+      fine_x[tx, ty] = f
+      cx[:, ty, tx] = (mx * stride[1] - ox * stride[1] + rng.integers(-9, 9),
+                       rng.integers(-50, 50))
+      off_x[tx, ty] = (int(rng.integers(-4, 4)), int(rng.integers(-4, 4)))
+    if ty + 1 < nt_y:
+      oy, ox = int(rng.integers(3, 6)), mx - int(rng.integers(0, 3))
+      f = np.full((4, oy, ox), 1.0, np.float32)
+      f[:2] = smooth((2, oy, ox), 5.0)
+      fine_y[tx, ty] = f
+      cy[:, ty, tx] = (rng.integers(-50, 50),
+                       my * stride[0] - oy * stride[0] + rng.integers(-9, 9))
+      off_y[tx, ty] = (int(rng.integers(-4, 4)), int(rng.integers(-4, 4)))
+  coarse = rng.standard_normal((2, nt_y, nt_x)) * 3
+  fx, fy, x, nbors, _ = stitch_elastic.aggregate_arrays(
+      (cx, fine_x, off_x), (cy, fine_y, off_y), coords, coarse, stride,
+      (my * int(stride[0]), mx * int(stride[1])))
+  return fx.astype(np.float32), fy.astype(np.float32), x.astype(np.float32), nbors, stride
+
+
 
 
 def synth_tile_pairs(num, size, seed, device):
@@ -492,6 +531,42 @@ def run_ours(args):
                 'h2d_bytes_per_step': 2 * 2 * local_nodes * 4,
                 'd2h_bytes_per_step': 2 * local_nodes * 4},
     }
+
+  # ---------------- stitching mesh of BASELINE config 2 (N = 1 only) ----------------
+  # 4 x 4 tiles of 4096^2 px at stride 40 -> [2, 16, 102, 102] tile meshes relaxed
+  # with the stitching prev_fn re-evaluated on the device in every step
+  # (stitch_elastic.compute_target_mesh, notebooks/em_stitching.ipynb:545-603).
+  if args.path in ('both', 'mesh') and world == 1 and rank == 0 and 'mesh' in result:
+    from sofima_b200 import stitch_elastic
+    fx, fy, sx0, nbors, sstride = synth_stitch(4, 4, (102, 102))
+    s_iters = args.mesh_iters
+    scfg = mesh.IntegrationConfig(
+        dt=0.001, gamma=0., k0=0.01, k=0.1, stride=sstride, num_iters=s_iters,
+        max_iters=s_iters, stop_v_max=0.0, dt_max=100, prefer_orig_order=True,
+        start_cap=0.1, final_cap=10., remove_drift=True)
+    prev_fn = stitch_elastic.target_mesh_fn(nbors, fx, fy, sstride)
+    xd = torch.from_numpy(sx0).to(dev)
+
+    def stitch_step(i):
+      mesh.relax_mesh(xd, None, scfg, prev_fn=prev_fn)
+
+    for i in range(W):
+      stitch_step(i)
+    s_ms, s_launches = timed(stitch_step, K)
+    s_nodes = sx0.shape[1] * sx0.shape[2] * sx0.shape[3]
+    t0 = time.perf_counter()
+    for i in range(K):
+      out, _, _ = mesh.relax_mesh(sx0, None, scfg, prev_fn=prev_fn)
+    s_e2e = (time.perf_counter() - t0) * 1e3
+    result['mesh']['stitching'] = {
+        'workload': f'config 2 mesh: [2,16,102,102] tile meshes, {s_iters} FIRE steps, '
+                    'stitching prev_fn evaluated on the device in every step',
+        'value': s_nodes * s_iters * K / (s_ms * 1e-3), 'unit': 'node-updates/s',
+        'us_per_integration_step': s_ms / K / s_iters * 1e3, 'gpu_launches': s_launches,
+        'e2e': {'value': s_nodes * s_iters * K / (s_e2e * 1e-3), 'unit': 'node-updates/s',
+                'h2d_bytes_per_step': int(sx0.nbytes + fx.nbytes + fy.nbytes),
+                'd2h_bytes_per_step': int(sx0.nbytes)},
+        'note': 'launch-latency bound (166 k nodes): two launches per integration step'}
 
   # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
