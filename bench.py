@@ -66,6 +66,31 @@ def _peaks():
 # ----------------------------------------------------------------------------------
 # synthetic data
 # ----------------------------------------------------------------------------------
+def synth_tile_grid(nt_x, nt_y, size, overlap=0.1, seed=1):
+  """nt_x x nt_y uint8 tiles cut from one texture with ~`overlap` nominal overlap and
+  +-20 px jitter, plus the coarse offset maps compute_flow_map expects."""
+  import scipy.ndimage as ndi
+  rng = np.random.default_rng(seed)
+  step = int(size * (1 - overlap))
+  big = (nt_y - 1) * step + size + 64, (nt_x - 1) * step + size + 64
+  tex = ndi.gaussian_filter(rng.standard_normal(big).astype(np.float32), 2.0)
+  tex = ((tex - tex.min()) / (tex.max() - tex.min()) * 255).astype(np.uint8)
+  pos = {(tx, ty): (ty * step + 32 + int(rng.integers(-20, 21)),
+                    tx * step + 32 + int(rng.integers(-20, 21)))
+         for tx in range(nt_x) for ty in range(nt_y)}
+  tiles = {k: np.ascontiguousarray(tex[y0:y0 + size, x0:x0 + size]) for k, (y0, x0) in pos.items()}
+  cxm = np.full((2, nt_y, nt_x), np.nan)
+  cym = np.full((2, nt_y, nt_x), np.nan)
+  for (tx, ty), (y0, x0) in pos.items():
+    if (tx + 1, ty) in pos:
+      y1, x1 = pos[tx + 1, ty]
+      cxm[:, ty, tx] = (x1 - x0 - size, y1 - y0)
+    if (tx, ty + 1) in pos:
+      y1, x1 = pos[tx, ty + 1]
+      cym[:, ty, tx] = (x1 - x0, y1 - y0 - size)
+  return tiles, cxm, cym
+
+
 def synth_stitch(nt_x, nt_y, mesh_shape, stride=(40.0, 40.0), seed=1):
   """Flow fields, coarse offsets and the neighbour table of an nt_x x nt_y tile grid
   with ~10 % overlap (3-5 flow columns / rows per seam), through aggregate_arrays."""
@@ -531,6 +556,34 @@ def run_ours(args):
                 'h2d_bytes_per_step': 2 * 2 * local_nodes * 4,
                 'd2h_bytes_per_step': 2 * local_nodes * 4},
     }
+
+  # ---------------- fine flow of BASELINE config 2 (N = 1 only) ----------------
+  # 4 x 4 grid of 4096^2 tiles with ~10 % overlap: stitch_elastic.compute_flow_map on the
+  # 12 horizontal + 12 vertical overlap strips (one flow_field call per tile pair, host
+  # tiles in, host flow fields out -- the reference's own call pattern).
+  if args.path in ('both', 'flow') and world == 1 and rank == 0 and 'metric' in result:
+    from sofima_b200 import stitch_elastic
+    grid_tiles, cxm, cym = synth_tile_grid(4, 4, FLOW_TILE)
+
+    def strips(i):
+      n = 0
+      for axis, cm in ((0, cxm), (1, cym)):
+        fl, _ = stitch_elastic.compute_flow_map(grid_tiles, cm, axis, (PATCH, PATCH),
+                                                (STEP, STEP), BATCH)
+        n += sum(int(np.isfinite(f[0]).sum()) for f in fl.values())
+      return n
+
+    strips(0)
+    t0 = time.perf_counter()
+    n_pairs = sum(strips(i) for i in range(2))
+    sec = time.perf_counter() - t0
+    result['config2_flow'] = {
+        'workload': 'stitch_elastic.compute_flow_map on the 24 overlap strips of a 4x4 grid '
+                    f'of {FLOW_TILE}^2 uint8 tiles, patch {PATCH}, step {STEP}; host tiles '
+                    'in, host flow fields out (e2e)',
+        'value': n_pairs / sec, 'unit': 'patch-pairs/s', 'patch_pairs_per_grid': n_pairs // 2,
+        'ms_per_grid': sec / 2 * 1e3}
+    del grid_tiles
 
   # ---------------- stitching mesh of BASELINE config 2 (N = 1 only) ----------------
   # 4 x 4 tiles of 4096^2 px at stride 40 -> [2, 16, 102, 102] tile meshes relaxed

@@ -2,6 +2,8 @@
 stitch_elastic.py): the per-step target mesh of elastic tile stitching.
 
   NeighborInfo             stitch_elastic.py:43-72
+  compute_flow_map         stitch_elastic.py:197-282   (host geometry + CUDA flow_field)
+  compute_flow_map3d       stitch_elastic.py:84-193
   aggregate_arrays         stitch_elastic.py:285-453   (host, NumPy -- as in the reference)
   compute_target_mesh      stitch_elastic.py:624-676   (CUDA, csrc/stitch.cuh)
   target_mesh_fn           the `prev_fn` closure the notebooks build around it
@@ -21,6 +23,8 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from . import _native
+from . import compat
+from . import flow_field
 from . import mesh as _mesh
 
 
@@ -37,6 +41,135 @@ class NeighborInfo(enum.IntEnum):
   coarse_offset_z = 8      # 3-d meshes only
   flow_size_z = 9
   fine_off_z = 10
+
+
+def _relative_intersection(box1, box2):
+  """The overlap of two boxes in the coordinates of each (stitch_elastic.py:75-81)."""
+  common = box1.intersection(box2)
+  return (compat.BoundingBox(start=common.start - box1.start, size=common.size),
+          compat.BoundingBox(start=common.start - box2.start, size=common.size))
+
+
+def compute_flow_map(tile_map: Mapping[tuple[int, int], np.ndarray], offset_map: np.ndarray,
+                     axis: int, patch_size: Sequence[int] = (120, 120),
+                     stride: Sequence[int] = (20, 20), batch_size: int = 256):
+  """Fine flow between horizontally (axis 0) or vertically (axis 1) adjacent 2-d tiles.
+
+  Same contract as stitch_elastic.compute_flow_map (stitch_elastic.py:197-282): the
+  overlap strips of the two tiles are cut so that they start at a multiple of `stride`
+  in the pre tile, the flow between them is estimated on the GPU, and the result is
+  NaN-padded by half a patch so that it is aligned with the mesh nodes.
+
+  Args:
+    tile_map: (x, y) -> tile image
+    offset_map: [2, y, x] coarse XY offset between tile (x, y) and its +axis neighbour
+    axis: 0 = neighbour at (x + 1, y), 1 = neighbour at (x, y + 1)
+    patch_size: YX patch size in pixels
+    stride: YX stride of the flow map in pixels
+    batch_size: flow vectors estimated per batch
+
+  Returns:
+    ((x, y) -> [4, fy, fx] flow, (x, y) -> XY offset the flow was computed with)
+  """
+  ny_t, nx_t = offset_map.shape[-2:]
+  calc = flow_field.JAXMaskedXCorrWithStatsCalculator()
+  step = tuple(int(v) for v in stride)
+  stride = np.asarray(step)
+  pad = [patch_size[0] // 2 // step[0], patch_size[1] // 2 // step[1]]
+  flows, offsets = {}, {}
+  for y in range(ny_t - axis):
+    for x in range(nx_t - (1 - axis)):
+      if np.isnan(offset_map[0, y, x]):
+        continue
+      pre = tile_map[x, y]
+      post = tile_map[x + (1 - axis), y + axis]
+      offset = offset_map[:, y, x]  # XY
+      rounded = stride[::-1] * np.round(offset / stride[::-1])
+      par = 1 - axis  # array axis along the tile-tile direction
+      overlap = -int(offset[axis])
+      overlap = pre.shape[par] - (pre.shape[par] - overlap) // stride[par] * stride[par]
+      ortho = int(rounded[1 - axis])
+
+      pre_sel = [slice(None), slice(None)]
+      post_sel = [slice(None), slice(None)]
+      pre_sel[par] = slice(-overlap, None)
+      post_sel[par] = slice(None, overlap)
+      if ortho > 0:    # post is shifted towards +ortho relative to pre
+        pre_sel[axis] = slice(ortho, None)
+        post_sel[axis] = slice(None, -ortho)
+      elif ortho < 0:
+        pre_sel[axis] = slice(None, ortho)
+        post_sel[axis] = slice(-ortho, None)
+      f = calc.flow_field(pre[tuple(pre_sel)], post[tuple(post_sel)],
+                          patch_size=tuple(patch_size), step=step, batch_size=batch_size)
+      # The inverse flow (post, pre) is -f: it is not computed separately.
+      flows[x, y] = np.pad(f, [[0, 0], [pad[0], pad[0] - 1], [pad[1], pad[1] - 1]],
+                           constant_values=np.nan)
+      offsets[x, y] = (-overlap, ortho) if axis == 0 else (ortho, -overlap)
+  return flows, offsets
+
+
+def compute_flow_map3d(tile_map: Mapping[tuple[int, int], np.ndarray],
+                       tile_shape: Sequence[int], offset_map: np.ndarray, axis: int,
+                       patch_size: Sequence[int] = (120, 120, 120),
+                       stride: Sequence[int] = (40, 40, 40), batch_size: int = 16):
+  """Fine flow between adjacent 3-d tiles (stitch_elastic.py:84-193).
+
+  Args:
+    tile_map: (x, y) -> [1, z, y, x] tile data
+    tile_shape: XYZ shape of a tile
+    offset_map: [3, 1, y, x] coarse XYZ offsets between (x, y) and its +axis neighbour
+    axis: 0 = x neighbour, 1 = y neighbour
+    patch_size, stride: ZYX, in pixels
+    batch_size: flow vectors estimated per batch
+
+  Returns:
+    ((x, y) -> [5, fz, fy, fx] flow, (x, y) -> XYZ offset the flow was computed with)
+  """
+  calc = flow_field.JAXMaskedXCorrWithStatsCalculator()
+  flows, offsets = {}, {}
+  ny_t, nx_t = offset_map.shape[-2:]
+  step = tuple(int(v) for v in stride)
+  pad = np.array(patch_size) // 2 // np.array(step)
+  tile_shape = tuple(int(v) for v in tile_shape)
+  s = step[2 - axis]
+  for y in range(ny_t - axis):
+    for x in range(nx_t - (1 - axis)):
+      coarse = offset_map[:, 0, y, x]  # XYZ
+      here = compat.BoundingBox(start=(0, 0, 0), size=tile_shape)
+      nbor = compat.BoundingBox(
+          start=(tile_shape[0] * (1 - axis) + coarse[0], tile_shape[1] * axis + coarse[1],
+                 coarse[2]), size=tile_shape)
+      isec_here, isec_nbor = _relative_intersection(here, nbor)
+      # Along the tile-tile direction the strip starts at a multiple of the stride
+      # inside the preceding tile ...
+      overlap = isec_here.size[axis]
+      aligned_start = (tile_shape[axis] - overlap) // s * s
+      shift = np.zeros(3)
+      shift[axis] = -((tile_shape[axis] - aligned_start) - overlap)
+      # ... and so do the starts in the two orthogonal directions.
+      for ax in range(3):
+        if ax == axis:
+          continue
+        if isec_here.start[ax] > 0:
+          shift[ax] = s * np.round(isec_here.start[ax] / s) - isec_here.start[ax]
+        elif isec_nbor.start[ax] > 0:
+          shift[ax] = -(s * np.round(isec_nbor.start[ax] / s) - isec_nbor.start[ax])
+      nbor = nbor.translate(shift)
+      isec_here, isec_nbor = _relative_intersection(here, nbor)
+      assert np.all(isec_here.start % s == 0)
+      assert np.all(isec_nbor.start % s == 0)
+      offset = np.array(nbor.start - here.start)
+      offset[axis] = -isec_here.size[axis]
+      offsets[x, y] = tuple(offset.tolist())
+      pre = tile_map[x, y][isec_here.to_slice4d()].squeeze(axis=0)
+      post = tile_map[x + (1 - axis), y + axis][isec_nbor.to_slice4d()].squeeze(axis=0)
+      assert pre.shape == post.shape
+      f = calc.flow_field(pre, post, patch_size=tuple(patch_size), step=step,
+                          batch_size=batch_size)
+      flows[x, y] = np.pad(f, [[0, 0]] + [[int(q), int(q) - 1] for q in pad],
+                           constant_values=np.nan)
+  return flows, offsets
 
 
 def aggregate_arrays(x_data, y_data, tile_coords: Sequence[tuple[int, int]],

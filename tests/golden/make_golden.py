@@ -344,6 +344,31 @@ def stitch_cases(mu, se):
   out['st2_relax_damped_x'], out['st2_relax_damped_ekin'] = (
       np.asarray(xr), np.asarray(ekin, dtype=np.float64))
 
+  # -- compute_flow_map (stitch_elastic.py:197-282): 3 x 2 tiles cut from one texture ----
+  tex = texture(21, (420, 560), sigma=1.5)
+  th, tw = 160, 200
+  nominal = {(tx, ty): (ty * 130 + [0, 4, -3][tx] * (ty > 0), tx * 170 + [0, -5][ty] * (tx > 0))
+             for tx in range(3) for ty in range(2)}
+  tiles = {k: np.ascontiguousarray(tex[y0:y0 + th, x0:x0 + tw]) for k, (y0, x0) in nominal.items()}
+  cxm = np.full((2, 2, 3), np.nan)
+  cym = np.full((2, 2, 3), np.nan)
+  for (tx, ty), (y0, x0) in nominal.items():
+    if (tx + 1, ty) in nominal:
+      y1, x1 = nominal[tx + 1, ty]
+      cxm[:, ty, tx] = (x1 - x0 - tw, y1 - y0)
+    if (tx, ty + 1) in nominal:
+      y1, x1 = nominal[tx, ty + 1]
+      cym[:, ty, tx] = (x1 - x0, y1 - y0 - th)
+  out['fm2_tex'] = tex
+  out['fm2_nominal'] = np.array([[tx, ty, y0, x0] for (tx, ty), (y0, x0) in nominal.items()])
+  out['fm2_cx'], out['fm2_cy'] = cxm, cym
+  for axis, cm in ((0, cxm), (1, cym)):
+    fl, of = se.compute_flow_map(tiles, cm, axis, patch_size=(32, 32), stride=(8, 8),
+                                 batch_size=64)
+    for k in fl:
+      out[f'fm2_flow{axis}_{k[0]}_{k[1]}'] = np.asarray(fl[k])
+      out[f'fm2_off{axis}_{k[0]}_{k[1]}'] = np.array(of[k])
+
   # -- 3-d stitching (LICONN): 2 x 2 tiles, mesh 4 x 6 x 7 nodes, stride (8, 20, 20) --
   stride3 = (8, 20, 20)
   coords3 = [(0, 0), (1, 0), (0, 1), (1, 1)]

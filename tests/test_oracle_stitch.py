@@ -124,3 +124,31 @@ def test_relaxation_3d_with_stitching_prev_fn_golden(g, tag, atol):
   assert t == 24
   np.testing.assert_allclose(x, g[f'{tag}_x'], rtol=0, atol=atol)
   np.testing.assert_allclose(e_kin, g[f'{tag}_ekin'], rtol=1e-6)
+
+
+def test_compute_flow_map_host_logic(g, monkeypatch):
+  # stitch_elastic.py:197-282: strip geometry / offsets / NaN padding of the product's
+  # compute_flow_map against the reference's own run (golden); the flow calculator is
+  # replaced by the oracle here (CPU), tests/test_stitch_gpu.py runs the CUDA one.
+  from oracle import flow_oracle
+  from sofima_b200 import flow_field, stitch_elastic
+  monkeypatch.setattr(flow_field, 'JAXMaskedXCorrWithStatsCalculator',
+                      flow_oracle.MaskedXCorrWithStatsCalculator)
+  _check_flow_maps(g, stitch_elastic)
+
+
+def _check_flow_maps(g, stitch_elastic):
+  tex = g['fm2_tex']
+  tiles = {(int(a), int(b)): np.ascontiguousarray(tex[y0:y0 + 160, x0:x0 + 200])
+           for a, b, y0, x0 in g['fm2_nominal']}
+  for axis, cm in ((0, g['fm2_cx']), (1, g['fm2_cy'])):
+    flows, offsets = stitch_elastic.compute_flow_map(tiles, cm, axis, patch_size=(32, 32),
+                                                     stride=(8, 8), batch_size=64)
+    assert len(flows) == len([k for k in g.files if k.startswith(f'fm2_flow{axis}_')])
+    for k, f in flows.items():
+      want = g[f'fm2_flow{axis}_{k[0]}_{k[1]}']
+      assert tuple(offsets[k]) == tuple(g[f'fm2_off{axis}_{k[0]}_{k[1]}'])
+      assert f.shape == want.shape
+      np.testing.assert_array_equal(np.isnan(f), np.isnan(want))
+      np.testing.assert_array_equal(f[:2], want[:2])
+      np.testing.assert_allclose(f[2:], want[2:], rtol=2e-3, atol=1e-6)

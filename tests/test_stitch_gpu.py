@@ -224,3 +224,45 @@ def test_prev_fn_errors(mods):
     mesh.relax_mesh(x, None, cfg, prev_fn=lambda a: a)
   with pytest.raises(ValueError):
     mesh.relax_mesh(x[:, :2], None, cfg, prev_fn=prev_fn)
+
+
+def test_compute_flow_map_golden(mods, g):
+  """stitch_elastic.compute_flow_map on the CUDA flow path vs the reference's run."""
+  from tests.test_oracle_stitch import _check_flow_maps
+  _check_flow_maps(g, mods[2])
+
+
+def test_config2_pipeline_vs_oracle(mods, g, monkeypatch):
+  """BASELINE config 2 in small: fine flow on the overlap strips -> aggregate_arrays ->
+  relaxation with the stitching prev_fn, CUDA vs the same pipeline on the oracle."""
+  from oracle import flow_oracle
+  from sofima_b200 import flow_field
+  _, mesh, stitch_elastic = mods
+  tex = g['fm2_tex']
+  coords = [(int(a), int(b)) for a, b, _, _ in g['fm2_nominal']]
+  tiles = {(int(a), int(b)): np.ascontiguousarray(tex[y0:y0 + 160, x0:x0 + 200])
+           for a, b, y0, x0 in g['fm2_nominal']}
+  stride = (8, 8)
+  cx3, cy3 = g['fm2_cx'], g['fm2_cy']
+
+  def pipeline(relax, target_fn):
+    fx, ox = stitch_elastic.compute_flow_map(tiles, cx3, 0, (32, 32), stride, 64)
+    fy, oy = stitch_elastic.compute_flow_map(tiles, cy3, 1, (32, 32), stride, 64)
+    afx, afy, x, nbors, _ = stitch_elastic.aggregate_arrays(
+        (cx3, fx, ox), (cy3, fy, oy), coords, np.zeros((2, 2, 3)), stride, (160, 200))
+    cfg = mesh.IntegrationConfig(dt=0.001, gamma=0., k0=0.01, k=0.1, stride=stride,
+                                 num_iters=20, max_iters=60, stop_v_max=0.0, dt_max=100,
+                                 prefer_orig_order=True, start_cap=0.1, final_cap=10.)
+    afx, afy = afx.astype(np.float32), afy.astype(np.float32)
+    return relax(x, None, cfg, prev_fn=target_fn(nbors, afx, afy, stride)), nbors, afx
+
+  (got, ek, t), nbors, afx = pipeline(mesh.relax_mesh, stitch_elastic.target_mesh_fn)
+  monkeypatch.setattr(flow_field, 'JAXMaskedXCorrWithStatsCalculator',
+                      flow_oracle.MaskedXCorrWithStatsCalculator)
+  oracle_fn = lambda nb, a, b, st: (lambda x: so.target_mesh_all(nb, x, a, b, st))
+  (want, ek_w, t_w), nbors_w, afx_w = pipeline(mo.relax_mesh, oracle_fn)
+  np.testing.assert_array_equal(nbors, nbors_w)
+  np.testing.assert_array_equal(afx, afx_w)      # integer flow vectors: identical
+  assert t == t_w == 60
+  np.testing.assert_array_equal(got, want)
+  assert np.abs(got).max() > 1e-4
