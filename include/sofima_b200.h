@@ -241,6 +241,22 @@ int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p,
                        const int32_t* pre_starts, const int32_t* post_starts,
                        int64_t batch, float* out_peaks);
 
+/* Optional accelerator for a series of sofima_xcorr_peaks / _images calls on the SAME
+ * image pair (one flow_field call, flow_field.py:610-697).  Patches of a regular flow
+ * grid overlap: the forward row transform of the raw pixels is computed once per image
+ * row and distinct patch x-start and shared by all patches; the per-patch mean
+ * (flow_field.py:340-353) and the flip of the post patch (:78-79) are applied, by
+ * linearity of the transform, when the column stage loads the spectra.  Unmasked 2-d
+ * patches on the two-pass transform lengths only.
+ *   pre_xstarts / post_xstarts: HOST arrays of the distinct (clamped) x starts.
+ * Later calls use the cache when images, shapes, dtype and patch widths match; a patch
+ * whose x start is not in the set yields NaN.  The image contents must not change
+ * while the cache is valid.  p == NULL drops the cache. */
+int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p,
+                          const void* pre_img, const void* post_img,
+                          const int32_t* pre_xstarts, int32_t n_pre,
+                          const int32_t* post_xstarts, int32_t n_post);
+
 /* Test hook: the raw correlation images of one batch, [batch, prod(pre+post-1)]
  * fp32 (what _batched_xcorr returns, flow_field.py:278-371). */
 int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p,

@@ -192,6 +192,9 @@ _PROTOS = {
     'sofima_xcorr_peaks': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_int64, _vp]),
+    'sofima_xcorr_rowcache': (ctypes.c_int, [
+        _vp, ctypes.POINTER(XcorrParams), _vp, _vp, ctypes.POINTER(ctypes.c_int32),
+        ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
     'sofima_xcorr_images': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_int64, _vp]),

@@ -35,6 +35,17 @@ struct sofima_ctx {
     cudaEvent_t e0, e1;
   };
   std::vector<Rec> recs;
+  // Row-spectra cache of the flow path (flow.cu: sofima_xcorr_rowcache): forward row
+  // transforms of every image row per distinct patch x-start, shared by all patches.
+  struct RowCache {
+    bool valid = false;
+    const void* img[2] = {nullptr, nullptr};
+    int dtype = 0, h[2] = {0, 0}, w[2] = {0, 0}, pw[2] = {0, 0}, L = 0;
+    float2* spec[2] = {nullptr, nullptr};    // [nxs][h][L / 2 + 1]
+    const int* xindex[2] = {nullptr, nullptr};  // [w]: x start -> slot, -1 = not cached
+    const float2* fix = nullptr;             // [3][L / 2 + 1]: rect(pre), rect(post), W(post)
+  } rowcache;
+  int rowfix_key[3] = {0, 0, 0};  // (L, pw pre, pw post) of the table in scratch "flow.rc_fix"
 };
 
 namespace sofima {

@@ -886,14 +886,33 @@ static void launch_rows_fwd_fast(sofima_ctx* ctx, const Problem& P, const float2
 }
 template <int N2>
 static void launch_cols_fast(sofima_ctx* ctx, const Problem& P, const float2* tw, const float2* T,
-                             float2* U) {
+                             float2* U, const RowCacheView* rc) {
   constexpr int C = FastLines<N2>::n;
+  constexpr int NT = C * FastDims<N2>::G;
   const dim3 grid(ceil_div(P.nkx, C), P.nb);
   const bool half = 2 * P.img[0].ph <= FastDims<N2>::L && 2 * P.img[1].ph <= FastDims<N2>::L;
-  if (half)
-    cols_fast<N2, C, true><<<grid, C * FastDims<N2>::G, 0, ctx->stream>>>(P, tw, T, U);
+  RowCacheView none;
+  memset(&none, 0, sizeof(none));
+  if (rc) {
+    if (half)
+      cols_fast<N2, C, true, true><<<grid, NT, 0, ctx->stream>>>(P, tw, T, U, *rc);
+    else
+      cols_fast<N2, C, false, true><<<grid, NT, 0, ctx->stream>>>(P, tw, T, U, *rc);
+  } else if (half) {
+    cols_fast<N2, C, true, false><<<grid, NT, 0, ctx->stream>>>(P, tw, T, U, none);
+  } else {
+    cols_fast<N2, C, false, false><<<grid, NT, 0, ctx->stream>>>(P, tw, T, U, none);
+  }
+}
+template <int N2>
+static void launch_rowspec_fast(sofima_ctx* ctx, const RowSpecJob& J, int slots, const float2* tw,
+                                float2* out) {
+  constexpr int TR = FastLines<N2>::n;
+  const dim3 grid(ceil_div((J.h + 1) / 2, TR), slots);
+  if (2 * J.pw <= FastDims<N2>::L)
+    rowspec_fast<N2, TR, true><<<grid, TR * FastDims<N2>::G, 0, ctx->stream>>>(J, tw, out);
   else
-    cols_fast<N2, C, false><<<grid, C * FastDims<N2>::G, 0, ctx->stream>>>(P, tw, T, U);
+    rowspec_fast<N2, TR, false><<<grid, TR * FastDims<N2>::G, 0, ctx->stream>>>(J, tw, out);
 }
 template <int N2>
 static void launch_rows_inv_fast(sofima_ctx* ctx, const Problem& P, const float2* tw,
@@ -1054,7 +1073,27 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   }
   const float scale = (float)(1.0 / ((double)Lx * (double)Ly));
 
-  if (!p->has_mean) {  // patch sums of the whole batch in one launch
+  // Row-spectra cache built by sofima_xcorr_rowcache for exactly these images?
+  RowCacheView rcv;
+  memset(&rcv, 0, sizeof(rcv));
+  const sofima_ctx::RowCache& rcache = ctx->rowcache;
+  bool cached = fast && rcache.valid && rcache.L == Lx && rcache.dtype == P.dtype;
+  for (int i = 0; i < 2 && cached; ++i)
+    cached = rcache.img[i] == P.img[i].data && rcache.h[i] == P.img[i].h &&
+             rcache.w[i] == P.img[i].w && rcache.pw[i] == P.img[i].pw;
+  if (cached) {
+    for (int i = 0; i < 2; ++i) {
+      rcv.spec[i] = rcache.spec[i];
+      rcv.xindex[i] = rcache.xindex[i];
+      rcv.h[i] = rcache.h[i];
+    }
+    rcv.fix = rcache.fix;
+    void* mb = nullptr;
+    if ((rc = scratch(ctx, "flow.rc_meta", sizeof(int4) * 2 * B, &mb))) return rc;
+    rcv.meta = static_cast<const int4*>(mb);
+  }
+  const bool dc_mean = cached && !p->has_mean && P.dtype == SOFIMA_U8;
+  if (!p->has_mean && !dc_mean) {  // patch sums of the whole batch in one launch
     for (long long b0 = 0; b0 < B; b0 += 65535) {
       P.b0 = b0;
       P.nb = (int)((B - b0 < 65535) ? (B - b0) : 65535);
@@ -1068,13 +1107,24 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       SOFIMA_CHECK_LAUNCH(ctx);
     }
   }
+  if (cached) {
+    LaunchTimer timer(ctx, "flow_mean");
+    const unsigned int mblocks = (unsigned int)ceil_div<long long>(2 * B * 32, 256);
+    if (dc_mean)
+      rowcache_meta_kernel<true><<<mblocks, 256, 0, ctx->stream>>>(
+          P, rcv, B, const_cast<int4*>(rcv.meta));
+    else
+      rowcache_meta_kernel<false><<<mblocks, 256, 0, ctx->stream>>>(
+          P, rcv, B, const_cast<int4*>(rcv.meta));
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
   for (long long b0 = 0; b0 < B; b0 += nsub) {
     const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
     P.b0 = b0;
     P.nb = nb;
     const int rp_max = (P.PY + 1) / 2;
     if (fast) {
-      {
+      if (!cached) {
         LaunchTimer timer(ctx, "flow_rows_fwd");
 #define CALL(N) launch_rows_fwd_fast<N>(ctx, P, Fx.tw, (float2*)Tbuf, rp_max)
         SOFIMA_N2_SWITCH(n2x, CALL)
@@ -1083,7 +1133,8 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       }
       {
         LaunchTimer timer(ctx, "flow_cols");
-#define CALL(N) launch_cols_fast<N>(ctx, P, Fy.tw, (const float2*)Tbuf, (float2*)Ubuf)
+#define CALL(N) \
+  launch_cols_fast<N>(ctx, P, Fy.tw, (const float2*)Tbuf, (float2*)Ubuf, cached ? &rcv : nullptr)
         SOFIMA_N2_SWITCH(n2y, CALL)
 #undef CALL
         SOFIMA_CHECK_LAUNCH(ctx);
@@ -1300,6 +1351,118 @@ static void peak_params(const sofima_xcorr_params* p, PeakParams* pp) {
 }  // namespace sofima
 
 extern "C" {
+
+int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                          const void* post_img, const int32_t* pre_xstarts, int32_t n_pre,
+                          const int32_t* post_xstarts, int32_t n_post) {
+  using namespace sofima;
+  using namespace sofima::flow;
+  if (!ctx) return fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
+  ctx->rowcache.valid = false;
+  if (!p) return SOFIMA_OK;  // clear only
+  int rc = check_params(ctx, p);
+  if (rc) return rc;
+  if (p->ndim != 2) return fail(ctx, SOFIMA_EUNSUPPORTED, "row cache: 2-d patches only");
+  if (!pre_img || !post_img || !pre_xstarts || !post_xstarts || n_pre < 1 || n_post < 1)
+    return fail(ctx, SOFIMA_EINVAL, "row cache: NULL / empty argument");
+  const int sx = p->pre_patch[1] + p->post_patch[1] - 1;
+  const int Lx = next_fast_len(sx);
+  const int Ly = next_fast_len(p->pre_patch[0] + p->post_patch[0] - 1);
+  int n2x = 0, n2y = 0;
+  if (!fast_n2(Lx, &n2x) || !fast_n2(Ly, &n2y))
+    return fail(ctx, SOFIMA_EUNSUPPORTED, "row cache: transform length %d x %d is not on the "
+                "two-pass path", Ly, Lx);
+  DeviceGuard guard(ctx->device);
+  const int nkx = Lx / 2 + 1;
+  const void* datas[2] = {pre_img, post_img};
+  const int64_t* shapes[2] = {p->pre_shape, p->post_shape};
+  const int pws[2] = {p->pre_patch[1], p->post_patch[1]};
+  const int32_t* xs[2] = {pre_xstarts, post_xstarts};
+  const int ns[2] = {n_pre, n_post};
+  size_t need = 0;
+  for (int i = 0; i < 2; ++i) need += (size_t)ns[i] * shapes[i][0] * nkx * sizeof(float2);
+  size_t have = 0;
+  for (const char* nm : {"flow.rowcache0", "flow.rowcache1"}) {
+    auto it = ctx->scratch.find(nm);
+    if (it != ctx->scratch.end()) have += it->second.bytes;
+  }
+  if (need > have) {
+    size_t free_b = 0, total_b = 0;
+    SOFIMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    if (need - have > free_b / 2)
+      return fail(ctx, SOFIMA_ENOMEM, "row cache of %zu MB does not fit", need >> 20);
+  }
+  FftPlan Fx;
+  if ((rc = make_plan(ctx, Lx, &Fx))) return rc;
+
+  sofima_ctx::RowCache c;
+  c.dtype = p->img_dtype;
+  c.L = Lx;
+  std::vector<int> table;
+  std::vector<float2> fix((size_t)3 * nkx);
+  const bool fix_ready = ctx->rowfix_key[0] == Lx && ctx->rowfix_key[1] == pws[0] &&
+                         ctx->rowfix_key[2] == pws[1];
+  for (int i = 0; i < 2; ++i) {
+    const int h = (int)shapes[i][0], w = (int)shapes[i][1], pw = pws[i];
+    c.img[i] = datas[i]; c.h[i] = h; c.w[i] = w; c.pw[i] = pw;
+    table.assign((size_t)w, -1);
+    for (int j = 0; j < ns[i]; ++j) {
+      if (xs[i][j] < 0 || xs[i][j] > w - pw)
+        return fail(ctx, SOFIMA_EINVAL, "row cache: x start %d out of range", xs[i][j]);
+      table[xs[i][j]] = j;
+    }
+    void *tb = nullptr, *xb = nullptr, *sb = nullptr;
+    const char* names[3][2] = {{"flow.rc_xindex0", "flow.rc_xindex1"},
+                               {"flow.rc_xstarts0", "flow.rc_xstarts1"},
+                               {"flow.rowcache0", "flow.rowcache1"}};
+    if ((rc = scratch(ctx, names[0][i], sizeof(int) * w, &tb))) return rc;
+    if ((rc = scratch(ctx, names[1][i], sizeof(int) * ns[i], &xb))) return rc;
+    if ((rc = scratch(ctx, names[2][i], (size_t)ns[i] * h * nkx * sizeof(float2), &sb))) return rc;
+    SOFIMA_CUDA(ctx, cudaMemcpyAsync(tb, table.data(), sizeof(int) * w, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    SOFIMA_CUDA(ctx, cudaMemcpyAsync(xb, xs[i], sizeof(int) * ns[i], cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `table` is reused
+    c.xindex[i] = static_cast<const int*>(tb);
+    c.spec[i] = static_cast<float2*>(sb);
+    RowSpecJob J;
+    J.data = datas[i]; J.dtype = p->img_dtype; J.h = h; J.w = w; J.pw = pw;
+    J.xstarts = static_cast<const int*>(xb);
+    {
+      LaunchTimer timer(ctx, "flow_rowspec");
+#define CALL(N) launch_rowspec_fast<N>(ctx, J, ns[i], Fx.tw, c.spec[i])
+      SOFIMA_N2_SWITCH(n2x, CALL)
+#undef CALL
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    // FFT of the pw-wide rect, and for the flipped post patch W[k] = exp(-2 pi i k (pw-1) / L)
+    for (int k = 0; k < nkx && !fix_ready; ++k) {
+      double re = 0.0, im = 0.0;
+      for (int n = 0; n < pw; ++n) {
+        const double ph = -2.0 * M_PI * (double)((long long)k * n % Lx) / Lx;
+        re += cos(ph);
+        im += sin(ph);
+      }
+      fix[(size_t)i * nkx + k] = make_float2((float)re, (float)im);
+      if (i == 1) {
+        const double ph = -2.0 * M_PI * (double)((long long)k * (pw - 1) % Lx) / Lx;
+        fix[(size_t)2 * nkx + k] = make_float2((float)cos(ph), (float)sin(ph));
+      }
+    }
+  }
+  void* fb = nullptr;
+  if ((rc = scratch(ctx, "flow.rc_fix", sizeof(float2) * fix.size(), &fb))) return rc;
+  if (!fix_ready) {
+    SOFIMA_CUDA(ctx, cudaMemcpyAsync(fb, fix.data(), sizeof(float2) * fix.size(),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->rowfix_key[0] = Lx; ctx->rowfix_key[1] = pws[0]; ctx->rowfix_key[2] = pws[1];
+  }
+  c.fix = static_cast<const float2*>(fb);
+  c.valid = true;
+  ctx->rowcache = c;
+  return SOFIMA_OK;
+}
 
 int sofima_xcorr_images(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
                         const void* post_img, const uint8_t* pre_mask,

@@ -158,13 +158,149 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
 }
 
 // ---------------------------------------------------------------------------------
+// Stage 1, shared form: patches of a regular flow grid overlap, so the same image row
+// segment [x0, x0 + pw) appears in ph / step patches.  By linearity
+//   FFT(row - mean * rect) = FFT(row) - mean * FFT(rect)
+// the forward row transform of the RAW pixels can be computed once per (image row,
+// distinct x0) and the per-patch mean applied when the column stage loads it; the
+// flipped post patch follows from FFT(reversed real row)[k] = W^k(pw-1) conj(FFT(row)[k]).
+// grid = (row-pair groups of the image, x-start slot), block = TR * G threads.
+// out: [slot][h][L / 2 + 1].
+// ---------------------------------------------------------------------------------
+struct RowSpecJob {
+  const void* data;
+  int dtype, h, w, pw;
+  const int* xstarts;  // [slots] device
+};
+
+template <int N2, int TR, bool HALF>
+__global__ void __launch_bounds__(TR * FastDims<N2>::G)
+rowspec_fast(RowSpecJob J, const float2* __restrict__ tw, float2* __restrict__ out) {
+  using D = FastDims<N2>;
+  constexpr int L = D::L;
+  constexpr int NT = TR * D::G;
+  constexpr int NKX = L / 2 + 1;
+  __shared__ float2 ex[TR * D::EXR];
+  __shared__ float2 xs[TR * D::PXP];
+  __shared__ float2 tw_s[L];
+  float* px = reinterpret_cast<float*>(xs);
+  const int rp0 = blockIdx.x * TR;
+  const int nrows = J.h, pw = J.pw;
+  if (2 * rp0 >= nrows) return;
+  for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
+  const int x0 = __ldg(&J.xstarts[blockIdx.y]);
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < 2 * TR; r += NT / 32) {
+      const int y = 2 * rp0 + r;
+      float* dst = px + r * D::PXP;
+      if (y >= nrows) {
+        for (int x = lane; x < pw; x += 32) dst[x] = 0.f;
+        continue;
+      }
+      const long long row = (long long)y * J.w + x0;
+      for (int x = lane; x < pw; x += 32) dst[x] = load_px(J.data, J.dtype, row + x);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TR * N2) {
+    const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
+    const float* r0 = px + (2 * f) * D::PXP;
+    const float* r1 = r0 + D::PXP;
+    float2 a[kN1];
+#pragma unroll
+    for (int n1 = 0; n1 < kN1; ++n1) {
+      const int x = N2 * n1 + n2;
+      if (HALF && n1 >= kN1 / 2) {
+        a[n1] = make_float2(0.f, 0.f);
+      } else {
+        a[n1] = (x < pw) ? make_float2(r0[x], r1[x]) : make_float2(0.f, 0.f);
+      }
+    }
+    Dft<kN1>::run(a);
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; ++k1)
+      ex[f * D::EXR + k1 * D::N2P + n2] = cmul(a[k1], tw_s[n2 * k1]);
+  }
+  __syncthreads();
+  if (threadIdx.x < TR * kN1) {
+    const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
+    float2 bq[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) bq[n2] = ex[f * D::EXR + k1 * D::N2P + n2];
+    Dft<N2>::run(bq);
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) xs[f * L + k1 + kN1 * k2] = bq[k2];
+  }
+  __syncthreads();
+  float2* ob = out + (size_t)blockIdx.y * nrows * NKX;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int f = warp; f < TR; f += NT / 32) {
+      const int y = 2 * (rp0 + f);
+      if (y >= nrows) continue;
+      const bool two = y + 1 < nrows;
+      for (int k = lane; k < NKX; k += 32) {
+        const float2 a = xs[f * L + k];
+        const float2 c = xs[f * L + (k == 0 ? 0 : L - k)];
+        ob[(size_t)y * NKX + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+        if (two)
+          ob[(size_t)(y + 1) * NKX + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+      }
+    }
+  }
+}
+
+struct RowCacheView {
+  const float2* spec[2];
+  const int* xindex[2];
+  const float2* fix;  // [3][nkx]
+  int h[2];
+  const int4* meta;   // [B][2]: {first cached row (lo, hi), mean bits, slot valid}
+};
+
+// Per (patch, image) record for the cached column stage, so that the column kernel
+// needs ONE load instead of the chain starts -> xindex -> spectra / partial sums.
+// One warp per (patch, image).  DC_MEAN: uint8 images -- the patch sum is the sum of the
+// DC bins of its cached rows (exact: integer sums below 2^24 survive the fp32 butterflies
+// unchanged), so the separate pass over the pixels is not needed.
+template <bool DC_MEAN>
+__global__ void rowcache_meta_kernel(Problem P, RowCacheView RC, long long B, int4* meta) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= 2 * B) return;
+  const long long b = i >> 1;
+  const int sl = (int)(i & 1);
+  const Image& I = P.img[sl];
+  const int y0 = clamp_start(P.starts[sl][b * 2 + 0], I.ph, I.h);
+  const int x0 = clamp_start(P.starts[sl][b * 2 + 1], I.pw, I.w);
+  const int slot = RC.xindex[sl][x0];
+  const long long first = (long long)(slot < 0 ? 0 : slot) * RC.h[sl] + y0;
+  float mean;
+  if (DC_MEAN) {
+    float s = 0.f;
+    const float2* col0 = RC.spec[sl] + first * P.nkx;
+    for (int y = lane; y < I.ph; y += 32) s += __ldg(&col0[(long long)y * P.nkx]).x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = __fdiv_rn(s, (float)(I.ph * I.pw));
+  } else {
+    mean = patch_mean(P, b, sl);
+  }
+  const long long row0 = sl == 0 ? first : first + I.ph - 1;
+  if (lane == 0)
+    meta[i] = make_int4((int)(row0 & 0xffffffffll), (int)(row0 >> 32), __float_as_int(mean),
+                        slot >= 0 ? 1 : 0);
+}
+
+// ---------------------------------------------------------------------------------
 // Stage 2: forward column FFTs of both patches, product, inverse column FFT.
 // grid = (column groups, pair), block = C * N2 threads (c fastest).
 // ---------------------------------------------------------------------------------
-template <int N2, int C, bool HALF>
+template <int N2, int C, bool HALF, bool CACHED>
 __global__ void __launch_bounds__(C * FastDims<N2>::G)
 cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T,
-          float2* __restrict__ U) {
+          float2* __restrict__ U, const RowCacheView RC) {
   using D = FastDims<N2>;
   constexpr int L = D::L;
   __shared__ float2 ex[C * D::EX];
@@ -176,11 +312,39 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
   const int r = threadIdx.x / C;  // n2 in pass-1 role, k1 in pass-2 role (r < 16)
   const bool col_ok = k0 + c < P.nkx;
   float2 prod[N2];
+  // cached form: all patch-level loads are issued up front (no dependent chains later)
+  int4 meta2[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+  float2 fix3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(1.f, 0.f)};
+  if (CACHED) {
+    meta2[0] = __ldg(&RC.meta[(P.b0 + blockIdx.y) * 2 + 0]);
+    meta2[1] = __ldg(&RC.meta[(P.b0 + blockIdx.y) * 2 + 1]);
+    if (col_ok) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) fix3[j] = __ldg(&RC.fix[j * P.nkx + k0 + c]);
+    }
+  }
 
 #pragma unroll
   for (int sl = 0; sl < 2; ++sl) {
     const int rows = P.img[sl].ph;
     const float2* Tb = T + ((size_t)sl * P.nb + blockIdx.y) * P.PY * P.nkx + k0 + c;
+    // Cached row spectra: row y of the patch is image row y0 + y (pre) resp.
+    // y0 + rows - 1 - y (post, flipped), slot = xindex[x0]; the mean and the x flip are
+    // applied here (see rowspec_fast).
+    long long cbase = 0, cstep = 0;
+    float mean = 0.f;
+    float2 rect = make_float2(0.f, 0.f), wk = make_float2(1.f, 0.f);
+    bool cached_ok = false;
+    if (CACHED) {
+      const int4 m = meta2[sl];
+      cached_ok = m.w != 0;
+      const long long row0 = ((long long)m.y << 32) | (unsigned int)m.x;
+      cbase = row0 * P.nkx + k0 + c;
+      cstep = sl == 0 ? P.nkx : -(long long)P.nkx;
+      mean = __int_as_float(m.z);
+      rect = fix3[sl];
+      wk = fix3[2];
+    }
     __syncthreads();  // twiddles staged / previous readers of ex done
     if (r < N2) {
       float2 a[kN1];
@@ -189,6 +353,20 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
         const int y = N2 * n1 + r;
         if (HALF && n1 >= kN1 / 2) {
           a[n1] = make_float2(0.f, 0.f);  // rows <= L / 2: pruned by constant folding
+        } else if (CACHED) {
+          float2 v = make_float2(0.f, 0.f);
+          if (col_ok && y < rows) {
+            if (cached_ok) {
+              const float2 s = __ldg(RC.spec[sl] + cbase + cstep * y);
+              // pre: s; post: W conj(s)
+              const float2 t = sl == 0 ? s : make_float2(wk.x * s.x + wk.y * s.y,
+                                                         wk.y * s.x - wk.x * s.y);
+              v = make_float2(t.x - mean * rect.x, t.y - mean * rect.y);
+            } else {
+              v = make_float2(__int_as_float(0x7fc00000), 0.f);  // x start not cached
+            }
+          }
+          a[n1] = v;
         } else {
           a[n1] = (col_ok && y < rows) ? __ldg(Tb + (size_t)y * P.nkx) : make_float2(0.f, 0.f);
         }

@@ -18,6 +18,7 @@ There is no CPU path here.
 from __future__ import annotations
 
 import collections.abc
+import os
 import ctypes
 import logging
 from typing import Callable, Iterator, Sequence, TypeVar
@@ -418,6 +419,19 @@ class _FlowJob:
     dev = torch.device('cuda', ctx.device)
     self.starts_d = torch.from_numpy(starts_h).to(dev).contiguous()  # [2, nb, B, nd]
     self.num_pairs = int(oyx.shape[0])
+    # Distinct patch x starts (clamped like the kernels' dynamic_slice) per image, for
+    # the shared row spectra (sofima_xcorr_rowcache).
+    self._xstarts = None
+    if nd == 2:
+      xs = []
+      for i, (shape, psz) in enumerate(((pre_shape, patch_size), (post_shape, post_patch_size))):
+        x = np.clip(starts_h[i, :, :, 1], 0, max(int(shape[1]) - int(psz[1]), 0))
+        xs.append(np.unique(x).astype(np.int32))
+      self._xstarts = xs
+      rows_direct = starts_h.shape[1] * starts_h.shape[2] * (patch_size[0] + post_patch_size[0])
+      rows_shared = len(xs[0]) * int(pre_shape[0]) + len(xs[1]) * int(post_shape[0])
+      spec_bytes = rows_shared * (sum(patch_size[1:]) + sum(post_patch_size[1:])) * 4 + 1
+      self._share_rows = (rows_shared < 0.6 * rows_direct and spec_bytes < (8 << 30))
 
   def run(self, pre_d, post_d, pre_m=None, post_m=None, mean=None, min_distance=2,
           peak_radius=5, progress_fn=_silent_fn, out=None):
@@ -432,12 +446,26 @@ class _FlowJob:
                         device=pre_d.device)
     self.ctx.bind_stream()
     lib = _native.lib()
-    for i in progress_fn(list(range(nb))):
-      rc = lib.sofima_xcorr_peaks(
+    cached = False
+    if (self._xstarts is not None and self._share_rows and pre_m is None and post_m is None
+        and os.environ.get('SOFIMA_FLOW_ROWCACHE', '1') != '0'):
+      # Overlapping patches share their forward row transforms (flow.cu).
+      xa, xb = self._xstarts
+      i32p = ctypes.POINTER(ctypes.c_int32)
+      rc = lib.sofima_xcorr_rowcache(
           self.ctx.handle, ctypes.byref(params), pre_d.data_ptr(), post_d.data_ptr(),
-          _ptr(pre_m), _ptr(post_m), self.starts_d[0, i].data_ptr(),
-          self.starts_d[1, i].data_ptr(), self.batch_size, out[i].data_ptr())
-      _native.check(self.ctx.handle, rc)
+          xa.ctypes.data_as(i32p), len(xa), xb.ctypes.data_as(i32p), len(xb))
+      cached = rc == _native.OK  # unsupported size / no memory: plain path
+    try:
+      for i in progress_fn(list(range(nb))):
+        rc = lib.sofima_xcorr_peaks(
+            self.ctx.handle, ctypes.byref(params), pre_d.data_ptr(), post_d.data_ptr(),
+            _ptr(pre_m), _ptr(post_m), self.starts_d[0, i].data_ptr(),
+            self.starts_d[1, i].data_ptr(), self.batch_size, out[i].data_ptr())
+        _native.check(self.ctx.handle, rc)
+    finally:
+      if cached:
+        lib.sofima_xcorr_rowcache(self.ctx.handle, None, None, None, None, 0, None, 0)
     return out
 
   def scatter(self, peaks: np.ndarray, output: np.ndarray):

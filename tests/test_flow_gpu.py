@@ -277,3 +277,37 @@ def test_full_size_properties(ff):
   np.testing.assert_array_equal(crop[:2], got[:2, :crop.shape[1], :crop.shape[2]])
   np.testing.assert_allclose(crop[2], got[2, :crop.shape[1], :crop.shape[2]],
                              rtol=1e-3)
+
+
+@pytest.mark.parametrize('dtype,post_patch,mean', [(np.uint8, None, None),
+                                                   (np.float32, 48, None),
+                                                   (np.uint8, None, 101.5)])
+def test_shared_row_spectra_match_plain_path(ff, monkeypatch, dtype, post_patch, mean):
+  """The shared-row-transform form (sofima_xcorr_rowcache: one forward row transform per
+  image row and patch x start, mean and post flip applied by linearity) against the
+  per-patch transforms and against the oracle."""
+  from sofima_b200 import _native
+  rng = np.random.default_rng(31)
+  base = ndi.gaussian_filter(rng.standard_normal((460, 520)), 1.5)
+  base = (base - base.min()) / (base.max() - base.min()) * 255
+  pre = np.ascontiguousarray(base[20:420, 30:500]).astype(dtype)
+  post = np.ascontiguousarray(base[24:424, 27:497]).astype(dtype)
+  if dtype == np.float32:
+    pre, post = pre / np.float32(3), post / np.float32(3)
+  calc = ff.JAXMaskedXCorrWithStatsCalculator(mean=mean)
+  kw = dict(patch_size=80 if post_patch else 64, step=16, batch_size=128,
+            post_patch_size=post_patch)  # 80 + 48 - 1 -> 128, 64 + 64 - 1 -> 128 = 16 x 8
+  ctx = _native.Context.get(0)
+  ctx.set_timing(True)
+  shared = calc.flow_field(pre, post, **kw)
+  rep = ctx.timing_report()
+  assert 'flow_rowspec' in rep and 'flow_rows_fwd' not in rep   # the shared form ran
+  monkeypatch.setenv('SOFIMA_FLOW_ROWCACHE', '0')
+  plain = calc.flow_field(pre, post, **kw)
+  rep = ctx.timing_report()
+  ctx.set_timing(False)
+  assert 'flow_rows_fwd' in rep and 'flow_rowspec' not in rep
+  _check_flow(shared, plain, stats_rtol=2e-4)
+  want = fo.MaskedXCorrWithStatsCalculator(mean=mean).flow_field(pre, post, **kw)
+  _check_flow(shared, want)
+  assert np.isfinite(shared[0]).mean() > 0.9
