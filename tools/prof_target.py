@@ -19,7 +19,7 @@ if which in ('mesh', 'both'):
 if which in ('flow', 'both'):
   tiles = bench.synth_tile_pairs(1, bench.FLOW_TILE, 100, dev)
   g = (bench.FLOW_TILE - 120) // 40
-  oyx = np.array(np.where(np.ones((g, g), bool))).T[:2048]
+  oyx = np.array(np.where(np.ones((g, g), bool))).T
   job = flow_field._FlowJob(ctx, oyx, (bench.FLOW_TILE,) * 2, (bench.FLOW_TILE,) * 2, (160, 160), (160, 160), (40, 40), 1024)
   for _ in range(2):
     job.run(tiles[0][0], tiles[0][1])
