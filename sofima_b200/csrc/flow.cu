@@ -28,7 +28,7 @@ namespace flow {
 
 constexpr int kThreads = 256;
 constexpr int kMaxStages = 12;
-constexpr int kMaxFftLen = 4096;
+constexpr int kMaxFftLen = 8192;
 
 struct FftPlan {
   int L;
@@ -426,6 +426,52 @@ cols_kernel(Problem P, FftPlan F, int C, Products pr, const float2* __restrict__
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------
+// Stage 2 for LONG columns (whole-strip correlations of the coarse tile offsets,
+// stitch_rigid.py:39-67: a 4096 x 300 strip gives 8192-point columns).  One line no
+// longer fits next to the spectra of all slots in shared memory, so the forward
+// spectra go through global memory: S layout [slot][pair][nkx][L] (lines contiguous).
+//   cols_fwd_long: grid (column, slot, pair);  cols_inv_long: grid (column, out, pair).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+cols_fwd_long_kernel(Problem P, FftPlan F, const float2* __restrict__ T,
+                     float2* __restrict__ S) {
+  extern __shared__ float2 smem[];
+  const int L = F.L;
+  float2* w0 = smem;
+  float2* w1 = w0 + L;
+  float2* tw_s = w1 + L;
+  load_twiddles(tw_s, F);
+  const int col = blockIdx.x, sl = blockIdx.y;
+  const int rows = P.img[P.slot[sl].src].ph;
+  const float2* Tb = T + ((size_t)sl * P.nb + blockIdx.z) * P.PY * P.nkx + col;
+  for (int y = threadIdx.x; y < L; y += kThreads)
+    w0[y] = y < rows ? Tb[(size_t)y * P.nkx] : make_float2(0.f, 0.f);
+  __syncthreads();
+  const float2* res = block_fft<false>(w0, w1, 1, F, tw_s);
+  float2* Sb = S + (((size_t)sl * P.nb + blockIdx.z) * P.nkx + col) * L;
+  for (int i = threadIdx.x; i < L; i += kThreads) Sb[i] = res[i];
+}
+
+__global__ void __launch_bounds__(kThreads)
+cols_inv_long_kernel(Problem P, FftPlan F, Products pr, const float2* __restrict__ S,
+                     float2* __restrict__ U) {
+  extern __shared__ float2 smem[];
+  const int L = F.L;
+  float2* w0 = smem;
+  float2* w1 = w0 + L;
+  float2* tw_s = w1 + L;
+  load_twiddles(tw_s, F);
+  const int col = blockIdx.x, o = blockIdx.y;
+  const float2* A = S + (((size_t)pr.a[o] * P.nb + blockIdx.z) * P.nkx + col) * L;
+  const float2* B = S + (((size_t)pr.b[o] * P.nb + blockIdx.z) * P.nkx + col) * L;
+  for (int i = threadIdx.x; i < L; i += kThreads) w0[i] = cmul(A[i], B[i]);
+  __syncthreads();
+  const float2* res = block_fft<true>(w0, w1, 1, F, tw_s);
+  float2* Ub = U + ((size_t)o * P.nb + blockIdx.z) * P.sy * P.nkx + col;
+  for (int y = threadIdx.x; y < P.sy; y += kThreads) Ub[(size_t)y * P.nkx] = res[y];
 }
 
 // ---------------------------------------------------------------------------------
@@ -1022,9 +1068,20 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   const size_t smem_rows = (size_t)(2 * R + 1) * Lx * sizeof(float2);
   int C = 8;
   while (C > 1 && (size_t)((2 + P.nslots) * C + 1) * Ly * sizeof(float2) > smem_cap) C /= 2;
-  const size_t smem_cols = (size_t)((2 + P.nslots) * C + 1) * Ly * sizeof(float2);
+  size_t smem_cols = (size_t)((2 + P.nslots) * C + 1) * Ly * sizeof(float2);
+  // Long columns: one line + work buffer + twiddles per block, spectra through global.
+  const bool long_cols = smem_cols > smem_cap;
+  if (long_cols) smem_cols = (size_t)3 * Ly * sizeof(float2);
   if (smem_rows > smem_cap || smem_cols > smem_cap)
     return fail(ctx, SOFIMA_EUNSUPPORTED, "patch too large for the shared-memory FFT");
+  if (long_cols) {
+    SOFIMA_CUDA(ctx, cudaFuncSetAttribute(cols_fwd_long_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_cap));
+    SOFIMA_CUDA(ctx, cudaFuncSetAttribute(cols_inv_long_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_cap));
+  }
   SOFIMA_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_cap));
@@ -1038,7 +1095,8 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   // Sub-batches of at most `scratch_mb` of spectra (T, U and the six masked outputs).
   const size_t per_pair = sizeof(float2) * ((size_t)P.nslots * P.PY * P.nkx +
                                             (size_t)pr.nout * P.sy * P.nkx) +
-                          (masked ? sizeof(float) * 6 * (size_t)P.sy * P.sx : 0);
+                          (masked ? sizeof(float) * 6 * (size_t)P.sy * P.sx : 0) +
+                          (long_cols ? sizeof(float2) * (size_t)P.nslots * P.nkx * Ly : 0);
   // Sub-batches bound the scratch memory only; measured on B200 the pipeline is fastest
   // when a whole reference batch (1024 pairs = 0.84 GB of spectra) goes through each
   // stage in one launch -- streaming T / U through HBM costs less than small grids.
@@ -1054,6 +1112,10 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
   if ((rc = scratch(ctx, "flow.U", sizeof(float2) * (size_t)pr.nout * nsub * P.sy * P.nkx,
                     &Ubuf))) return rc;
   if ((rc = scratch(ctx, "flow.means", sizeof(MeanPartial) * 2 * kMeanGroups * B, &means)))
+    return rc;
+  void* Sbuf = nullptr;
+  if (long_cols &&
+      (rc = scratch(ctx, "flow.S", sizeof(float2) * (size_t)P.nslots * nsub * P.nkx * Ly, &Sbuf)))
     return rc;
   P.parts = static_cast<const MeanPartial*>(means);
   P.has_mean = p->has_mean;
@@ -1164,7 +1226,15 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
                         ctx->stream>>>(P, Fx, R, (float2*)Tbuf);
       SOFIMA_CHECK_LAUNCH(ctx);
     }
-    {
+    if (long_cols) {
+      LaunchTimer timer(ctx, "flow_cols");
+      cols_fwd_long_kernel<<<dim3(P.nkx, P.nslots, nb), kThreads, smem_cols, ctx->stream>>>(
+          P, Fy, (const float2*)Tbuf, (float2*)Sbuf);
+      SOFIMA_CHECK_LAUNCH(ctx);
+      cols_inv_long_kernel<<<dim3(P.nkx, pr.nout, nb), kThreads, smem_cols, ctx->stream>>>(
+          P, Fy, pr, (const float2*)Sbuf, (float2*)Ubuf);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    } else {
       LaunchTimer timer(ctx, "flow_cols");
       cols_kernel<<<dim3(ceil_div(P.nkx, C), nb), kThreads, smem_cols, ctx->stream>>>(
           P, Fy, C, pr, (const float2*)Tbuf, (float2*)Ubuf);

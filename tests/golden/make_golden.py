@@ -369,6 +369,12 @@ def stitch_cases(mu, se):
       out[f'fm2_flow{axis}_{k[0]}_{k[1]}'] = np.asarray(fl[k])
       out[f'fm2_off{axis}_{k[0]}_{k[1]}'] = np.array(of[k])
 
+  # -- compute_coarse_offsets (stitch_rigid.py:104-273) on the same tile grid ----------
+  sr = shim.load_reference('stitch_rigid')
+  cox, coy = sr.compute_coarse_offsets((2, 3), tiles, overlaps_xy=((30, 44), (30, 44)),
+                                       min_range=(10, 100, 0), min_overlap=16, filter_size=5)
+  out['co_conn_x'], out['co_conn_y'] = np.asarray(cox), np.asarray(coy)
+
   # -- 3-d stitching (LICONN): 2 x 2 tiles, mesh 4 x 6 x 7 nodes, stride (8, 20, 20) --
   stride3 = (8, 20, 20)
   coords3 = [(0, 0), (1, 0), (0, 1), (1, 1)]

@@ -152,3 +152,26 @@ def _check_flow_maps(g, stitch_elastic):
       np.testing.assert_array_equal(np.isnan(f), np.isnan(want))
       np.testing.assert_array_equal(f[:2], want[:2])
       np.testing.assert_allclose(f[2:], want[2:], rtol=2e-3, atol=1e-6)
+
+
+def _check_coarse_offsets(g, stitch_rigid):
+  tex = g['fm2_tex']
+  tiles = {(int(a), int(b)): np.ascontiguousarray(tex[y0:y0 + 160, x0:x0 + 200])
+           for a, b, y0, x0 in g['fm2_nominal']}
+  cx, cy = stitch_rigid.compute_coarse_offsets(
+      (2, 3), tiles, overlaps_xy=((30, 44), (30, 44)), min_range=(10, 100, 0),
+      min_overlap=16, filter_size=5)
+  np.testing.assert_array_equal(cx, g['co_conn_x'])
+  np.testing.assert_array_equal(cy, g['co_conn_y'])
+  np.testing.assert_array_equal(cx[:, 0], g['fm2_cx'])  # = the true tile offsets
+  np.testing.assert_array_equal(cy[:, 0], g['fm2_cy'])
+
+
+def test_compute_coarse_offsets_host_logic(g, monkeypatch):
+  # stitch_rigid.py:104-273 against the reference's own run (golden); the correlation
+  # itself is the oracle's here, tests/test_stitch_gpu.py runs the CUDA one.
+  from oracle import flow_oracle
+  from sofima_b200 import flow_field, stitch_rigid
+  monkeypatch.setattr(flow_field, 'JAXMaskedXCorrWithStatsCalculator',
+                      flow_oracle.MaskedXCorrWithStatsCalculator)
+  _check_coarse_offsets(g, stitch_rigid)

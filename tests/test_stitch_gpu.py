@@ -266,3 +266,37 @@ def test_config2_pipeline_vs_oracle(mods, g, monkeypatch):
   assert t == t_w == 60
   np.testing.assert_array_equal(got, want)
   assert np.abs(got).max() > 1e-4
+
+
+def test_compute_coarse_offsets_golden(mods, g):
+  """stitch_rigid.compute_coarse_offsets (whole-strip masked correlations on the GPU)
+  vs the reference's run."""
+  from sofima_b200 import stitch_rigid
+  from tests.test_oracle_stitch import _check_coarse_offsets
+  _check_coarse_offsets(g, stitch_rigid)
+
+
+@pytest.mark.parametrize('shape,shift', [((1500, 100), (7, -3)), ((120, 1600), (-4, 9)),
+                                         ((4096, 300), (11, 5))])
+def test_whole_strip_masked_correlation(mods, shape, shift):
+  """One masked correlation of a whole overlap strip (stitch_rigid.py:39-67): transform
+  lengths up to 8192 x 600 -- the long-column / long-row form of the flow kernels."""
+  import scipy.ndimage as ndi
+  from oracle import flow_oracle
+  from sofima_b200 import flow_field
+  rng = np.random.default_rng(shape[0])
+  h, w = shape
+  base = ndi.gaussian_filter(rng.standard_normal((h + 40, w + 40)), 2.0)
+  base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+  a = np.ascontiguousarray(base[20:20 + h, 20:20 + w])
+  b = np.ascontiguousarray(base[20 + shift[0]:20 + shift[0] + h, 20 + shift[1]:20 + shift[1] + w])
+  am = rng.random(shape) < 0.05
+  bm = rng.random(shape) < 0.05
+  am[: h // 7, : w // 3] = True
+  kw = dict(pre_mask=am, post_mask=bm, patch_size=shape, step=(1, 1), batch_size=1)
+  got = flow_field.JAXMaskedXCorrWithStatsCalculator().flow_field(a, b, **kw)
+  want = flow_oracle.MaskedXCorrWithStatsCalculator().flow_field(a, b, **kw)
+  assert got.shape == want.shape == (4, 1, 1)
+  np.testing.assert_array_equal(got[:2], want[:2])
+  np.testing.assert_array_equal(got[:2, 0, 0], (shift[1], shift[0]))
+  np.testing.assert_allclose(got[2:], want[2:], rtol=5e-3, atol=1e-6)
