@@ -621,6 +621,61 @@ def run_ours(args):
                 'd2h_bytes_per_step': int(sx0.nbytes)},
         'note': 'launch-latency bound (166 k nodes): two launches per integration step'}
 
+  # ---------------- widened rows, N = 1 only ----------------
+  if world == 1 and rank == 0 and args.path == 'both':
+    from sofima_b200 import map_utils
+    from oracle import stitch_oracle, flow_oracle
+    widened = {}
+    # f-1 compose_maps_fast: 8 sections of 1024^2 nodes, stride 40 (HBM: read map1 and
+    # map2 once, write the result = 24 B per node).
+    rngw = np.random.default_rng(5)
+    m1 = torch.from_numpy((rngw.standard_normal((2, 8, 1024, 1024)) * 20).astype(np.float32)).to(dev)
+    m2 = torch.from_numpy((rngw.standard_normal((2, 8, 1024, 1024)) * 5).astype(np.float32)).to(dev)
+    cm = lambda i: map_utils.compose_maps_fast(m1, (0, 0, 0), 40.0, m2, (0, 3, 2), 40.0)
+    for i in range(W):
+      cm(i)
+    c_ms, _ = timed(cm, 20)
+    c_nodes = 8 * 1024 * 1024
+    c_gbs = c_nodes * 24 / (c_ms / 20 * 1e-3) / 1e9
+    sm1, sm2 = m1[:, :1, :512, :512].cpu().numpy(), m2[:, :1, :512, :512].cpu().numpy()
+    t0 = time.perf_counter()
+    stitch_oracle.compose_maps_fast(sm1, (0, 0, 0), 40.0, sm2, (0, 3, 2), 40.0)
+    c_cpu = 512 * 512 / (time.perf_counter() - t0)
+    widened['compose_maps_fast'] = {
+        'workload': 'map_utils.compose_maps_fast, [2,8,1024,1024] maps, stride 40, HBM-resident',
+        'value': c_nodes / (c_ms / 20 * 1e-3), 'unit': 'nodes/s', 'us_per_call': c_ms / 20 * 1e3,
+        'roofline': {'bound': 'hbm', 'achieved': c_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': c_gbs / peaks['hbm_gbs'], 'traffic': None,
+                     'peak_source': peaks['source'],
+                     'algorithmic_bytes_per_node': 24},
+        'cpu_baseline': {'value': c_cpu, 'unit': 'nodes/s', 'cores': 1, 'kind': 'port',
+                         'sample': 'one 512^2 section, oracle/stitch_oracle.py (NumPy)'}}
+    del m1, m2
+    # f-2 whole-strip masked correlation (stitch_rigid._estimate_offset): one 4096 x 300
+    # strip pair with masks, host arrays in, offset out (e2e).
+    strip = synth_tile_pairs(1, FLOW_TILE, 41, torch.device('cpu'))[0]
+    sa = np.ascontiguousarray(strip[0].numpy()[:, -300:])
+    sb = np.ascontiguousarray(strip[1].numpy()[:, -300:])  # same region, shifted by (3, -4)
+    ma = rngw.random(sa.shape) < 0.05
+    mb = rngw.random(sb.shape) < 0.05
+    kw = dict(pre_mask=ma, post_mask=mb, patch_size=sa.shape, step=(1, 1), batch_size=1)
+    calc.flow_field(sa, sb, **kw)
+    t0 = time.perf_counter()
+    for i in range(5):
+      calc.flow_field(sa, sb, **kw)
+    s_ms = (time.perf_counter() - t0) / 5 * 1e3
+    t0 = time.perf_counter()
+    flow_oracle.MaskedXCorrWithStatsCalculator().flow_field(sa, sb, **kw)
+    s_cpu_ms = (time.perf_counter() - t0) * 1e3
+    widened['whole_strip_masked_xcorr'] = {
+        'workload': 'one masked correlation of a 4096 x 300 overlap strip pair '
+                    '(8192 x 600-point transforms, Padfield normalisation, peak), e2e',
+        'value': 1e3 / s_ms, 'unit': 'strip-pairs/s', 'ms_per_strip_pair': s_ms,
+        'cpu_baseline': {'value': 1e3 / s_cpu_ms, 'unit': 'strip-pairs/s',
+                         'cores': len(os.sched_getaffinity(0)), 'kind': 'port',
+                         'sample': 'the same strip pair, oracle/flow_oracle.py (pocketfft)'}}
+    result['widened'] = widened
+
   # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     cores = len(os.sched_getaffinity(0))

@@ -190,12 +190,12 @@ __device__ __forceinline__ void linear_nodes(float c, int size, bool constant_mo
 
 template <int DIM>
 __global__ void __launch_bounds__(kThreads) compose_maps_kernel(const ComposeParams q) {
+  // grid = (x blocks, y, z): no index divisions
   const long long n = (long long)q.n1[0] * q.n1[1] * q.n1[2];
-  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
-  const int x = (int)(i % q.n1[2]);
-  const int y = (int)((i / q.n1[2]) % q.n1[1]);
-  const int z = (int)(i / ((long long)q.n1[2] * q.n1[1]));
+  const int x = blockIdx.x * kThreads + threadIdx.x;
+  const int y = blockIdx.y, z = blockIdx.z;
+  if (x >= q.n1[2]) return;
+  const long long i = ((long long)z * q.n1[1] + y) * q.n1[2] + x;
   const long long cs2 = (long long)q.n2[0] * q.n2[1] * q.n2[2];
   const float qnan = __int_as_float(0x7fc00000);
   const bool cm = q.constant_mode != 0;
