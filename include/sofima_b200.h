@@ -211,7 +211,7 @@ int sofima_shard_destroy(sofima_mesh_shard* shard);
  *  Patch flow  (reference: flow_field.py)
  * ------------------------------------------------------------------------- */
 
-enum { SOFIMA_U8 = 0, SOFIMA_F32 = 1 };
+enum { SOFIMA_U8 = 0, SOFIMA_F32 = 1, SOFIMA_U16 = 2, SOFIMA_U32 = 3 /* warp only */ };
 
 typedef struct {
   int32_t ndim;            /* 2 or 3 */
@@ -273,6 +273,26 @@ int sofima_batched_peaks(sofima_ctx* ctx, int ndim, const float* img,
                          const int32_t* center_offset, int min_distance,
                          float threshold_rel, const int32_t* peak_radius,
                          float* out_peaks);
+
+/* ============================================================================
+ *  Image warping  (reference: warp.py)
+ * ========================================================================== */
+
+/* Replaces the per-voxel work of warp.ndimage_warp (warp.py:189-335): every output
+ * voxel interpolates the coordinate map at (index - offset) / stride (warp.py:300-306)
+ * and samples the image there (warp.py:309), both exactly as
+ * scipy.ndimage.map_coordinates(order, mode='constant', cval=0) in float64.
+ *   dim 2 or 3; shapes / offset / stride hold `dim` values in [z]yx order
+ *   image: device, img_dtype SOFIMA_U8 | _U16 | _U32 | _F32, image_shape
+ *   src_map: device float64 [dim, *map_shape], the map in ABSOLUTE source voxel units
+ *            (map_utils.to_absolute + box offset + out_scale, warp.py:245-260; the host
+ *            side prepares it exactly as the reference does)
+ *   order: 0 (nearest) or 1 (linear); out: device, same dtype as image, out_shape */
+int sofima_warp_image(sofima_ctx* ctx, int dim, const void* image, int img_dtype,
+                      const int64_t* image_shape, const double* src_map,
+                      const int64_t* map_shape, const double* offset,
+                      const double* stride, int order, void* out,
+                      const int64_t* out_shape);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ SOURCES = {
     'ctx.cu': [],
     'mesh.cu': ['-fmad=false'],
     'flow.cu': [],
+    'warp.cu': ['-fmad=false'],  # float64 arithmetic identical to SciPy's
 }
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, 1, 2, 3, 4
@@ -192,6 +193,10 @@ _PROTOS = {
     'sofima_xcorr_peaks': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_int64, _vp]),
+    'sofima_warp_image': (ctypes.c_int, [
+        _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), _vp,
+        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double),
+        ctypes.POINTER(ctypes.c_double), ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64)]),
     'sofima_xcorr_rowcache': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, ctypes.POINTER(ctypes.c_int32),
         ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
