@@ -674,6 +674,41 @@ def run_ours(args):
         'cpu_baseline': {'value': 1e3 / s_cpu_ms, 'unit': 'strip-pairs/s',
                          'cores': len(os.sched_getaffinity(0)), 'kind': 'port',
                          'sample': 'the same strip pair, oracle/flow_oracle.py (pocketfft)'}}
+    # f-3 warp.ndimage_warp: one 8192^2 uint8 image through a 206^2-node map (stride 40),
+    # order 1; device image in, device image out.  HBM: read + write the image = 2 B / px.
+    from sofima_b200 import warp as warp_mod
+    from oracle import warp_oracle
+    import scipy.ndimage as ndi
+    wimg = torch.randint(0, 255, (8192, 8192), dtype=torch.uint8, device=dev)
+    wmap = np.stack([ndi.gaussian_filter(rngw.standard_normal((206, 206)), 6) * 400,
+                     ndi.gaussian_filter(rngw.standard_normal((206, 206)), 6) * 400])
+    wf = lambda i: warp_mod.ndimage_warp(wimg, wmap, (40, 40), (1024, 1024), (0, 0))
+    for i in range(W):
+      wf(i)
+    ctx.set_timing(True)
+    w_ms, _ = timed(wf, 10)
+    w_rep = ctx.timing_report()
+    ctx.set_timing(False)
+    w_kernel_ms = w_rep['warp_image']['ms'] / w_rep['warp_image']['n']
+    w_gbs = 2 * 8192 * 8192 / (w_kernel_ms * 1e-3) / 1e9
+    crop = wimg[:1024, :1024].cpu().numpy()
+    t0 = time.perf_counter()
+    warp_oracle.ndimage_warp(crop, wmap[:, :27, :27], (40, 40))
+    w_cpu = 1024 * 1024 / (time.perf_counter() - t0)
+    widened['ndimage_warp'] = {
+        'workload': 'warp.ndimage_warp, 8192^2 uint8 image, 206^2-node map (stride 40), '
+                    'order 1, device image in / out',
+        'value': 8192 * 8192 / (w_ms / 10 * 1e-3), 'unit': 'pixels/s',
+        'ms_per_image': w_ms / 10, 'kernel_ms': w_kernel_ms,
+        'roofline': {'bound': 'hbm', 'achieved': w_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': w_gbs / peaks['hbm_gbs'], 'traffic': None,
+                     'peak_source': peaks['source'], 'algorithmic_bytes_per_pixel': 2,
+                     'note': 'float64 arithmetic per pixel (bit-exact vs SciPy) bounds the '
+                             'kernel, not HBM'},
+        'cpu_baseline': {'value': w_cpu, 'unit': 'pixels/s', 'cores': 1, 'kind': 'port',
+                         'sample': 'one 1024^2 crop, oracle/warp_oracle.py (NumPy float64, '
+                                   '== scipy.ndimage.map_coordinates)'}}
+    del wimg
     result['widened'] = widened
 
   # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
