@@ -324,24 +324,37 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
     }
   }
 
+  // Cached row spectra: row y of the patch is image row y0 + y (pre) resp.
+  // y0 + rows - 1 - y (post, flipped), slot = xindex[x0]; the mean and the x flip are
+  // applied after the load (see rowspec_fast).  The raw spectra of the post patch are
+  // requested while the pre patch is still being transformed (software pipelining: the
+  // loads were half of this kernel's stalls).
+  constexpr int NLOAD = HALF ? kN1 / 2 : kN1;
+  float2 raw[NLOAD];
+  auto load_raw = [&](int sl) {
+    const int rows = P.img[sl].ph;
+    const int4 m = meta2[sl];
+    const long long row0 = ((long long)m.y << 32) | (unsigned int)m.x;
+    const long long cbase = row0 * P.nkx + k0 + c;
+    const long long cstep = sl == 0 ? P.nkx : -(long long)P.nkx;
+#pragma unroll
+    for (int n1 = 0; n1 < NLOAD; ++n1) {
+      const int y = N2 * n1 + r;
+      raw[n1] = (col_ok && y < rows && m.w != 0) ? __ldg(RC.spec[sl] + cbase + cstep * y)
+                                                : make_float2(0.f, 0.f);
+    }
+  };
+  if (CACHED && r < N2) load_raw(0);
 #pragma unroll
   for (int sl = 0; sl < 2; ++sl) {
     const int rows = P.img[sl].ph;
     const float2* Tb = T + ((size_t)sl * P.nb + blockIdx.y) * P.PY * P.nkx + k0 + c;
-    // Cached row spectra: row y of the patch is image row y0 + y (pre) resp.
-    // y0 + rows - 1 - y (post, flipped), slot = xindex[x0]; the mean and the x flip are
-    // applied here (see rowspec_fast).
-    long long cbase = 0, cstep = 0;
     float mean = 0.f;
     float2 rect = make_float2(0.f, 0.f), wk = make_float2(1.f, 0.f);
     bool cached_ok = false;
     if (CACHED) {
-      const int4 m = meta2[sl];
-      cached_ok = m.w != 0;
-      const long long row0 = ((long long)m.y << 32) | (unsigned int)m.x;
-      cbase = row0 * P.nkx + k0 + c;
-      cstep = sl == 0 ? P.nkx : -(long long)P.nkx;
-      mean = __int_as_float(m.z);
+      cached_ok = meta2[sl].w != 0;
+      mean = __int_as_float(meta2[sl].z);
       rect = fix3[sl];
       wk = fix3[2];
     }
@@ -357,7 +370,7 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
           float2 v = make_float2(0.f, 0.f);
           if (col_ok && y < rows) {
             if (cached_ok) {
-              const float2 s = __ldg(RC.spec[sl] + cbase + cstep * y);
+              const float2 s = raw[n1 < NLOAD ? n1 : 0];
               // pre: s; post: W conj(s)
               const float2 t = sl == 0 ? s : make_float2(wk.x * s.x + wk.y * s.y,
                                                          wk.y * s.x - wk.x * s.y);
@@ -375,6 +388,7 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
 #pragma unroll
       for (int k1 = 0; k1 < kN1; ++k1)
         ex[c * D::EX + k1 * D::N2P + r] = cmul(a[k1], tw_s[r * k1]);
+      if (CACHED && sl == 0) load_raw(1);  // in flight during pass 2 of the pre patch
     }
     __syncthreads();
     if (r < kN1) {
