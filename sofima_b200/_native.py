@@ -16,7 +16,8 @@ from typing import Sequence
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, '_lib')
-LIB_PATH = os.path.join(LIB_DIR, 'libsofima_b200.so')
+# SOFIMA_B200_LIB: load another build of the same C ABI (kernel A/B measurements).
+LIB_PATH = os.environ.get('SOFIMA_B200_LIB') or os.path.join(LIB_DIR, 'libsofima_b200.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC_ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']

@@ -2,7 +2,8 @@
 //
 // For transform lengths L = 16 * N2 (N2 in {8,10,12,15,16,20,24,25,32}; L = 320 for
 // the EM default patch 160) each 1-d FFT is done in exactly two passes with all
-// butterflies in registers (generated codelets, fft_codelets.cuh):
+// butterflies in registers (generated codelets on packed fp32x2 instructions,
+// fft_codelets.cuh):
 //
 //   forward  x[N2 n1 + n2] -> X[k1 + 16 k2]:
 //     pass 1  thread n2 : 16-point DFT over n1, twiddle W_L^(n2 k1)
@@ -42,6 +43,21 @@ struct FastDims {
 
 __device__ __forceinline__ float2 swap_ri(float2 a) { return make_float2(a.y, a.x); }
 
+// Twiddle table -> shared memory with asynchronous copies (LDGSTS): a plain load ->
+// shared-store pair at the top of a kernel stalls the thread for one L2 round trip before
+// it can request its spectra from HBM; the asynchronous copy needs no register and no
+// scoreboard wait.  stage_twiddles_wait() + __syncthreads() must precede the first use.
+template <int L, int NT>
+__device__ __forceinline__ void stage_twiddles(float2* tw_s, const float2* __restrict__ tw) {
+  for (int i = threadIdx.x; i < L; i += NT) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(tw_s + i);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(tw + i) : "memory");
+  }
+}
+__device__ __forceinline__ void stage_twiddles_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------
 // Stage 1: forward row FFTs (two real rows per complex transform).
 // grid = (row-pair groups, slot, pair), block = TR * N2 threads.
@@ -63,7 +79,7 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
   const int rp0 = blockIdx.x * TR;
   const int nrows = I.ph, pw = I.pw;
   if (2 * rp0 >= nrows) return;
-  for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
+  stage_twiddles<L, NT>(tw_s, tw);
 
   const int y0 = clamp_start(P.starts[sl.src][b * 2 + 0], I.ph, I.h);
   const int x0 = clamp_start(P.starts[sl.src][b * 2 + 1], I.pw, I.w);
@@ -105,6 +121,7 @@ rows_fwd_fast(Problem P, const float2* __restrict__ tw, float2* __restrict__ T) 
       }
     }
   }
+  stage_twiddles_wait();
   __syncthreads();
 
   if (threadIdx.x < TR * N2) {  // pass 1: thread (f, n2)
@@ -187,7 +204,7 @@ rowspec_fast(RowSpecJob J, const float2* __restrict__ tw, float2* __restrict__ o
   const int rp0 = blockIdx.x * TR;
   const int nrows = J.h, pw = J.pw;
   if (2 * rp0 >= nrows) return;
-  for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
+  stage_twiddles<L, NT>(tw_s, tw);
   const int x0 = __ldg(&J.xstarts[blockIdx.y]);
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,6 +219,7 @@ rowspec_fast(RowSpecJob J, const float2* __restrict__ tw, float2* __restrict__ o
       for (int x = lane; x < pw; x += 32) dst[x] = load_px(J.data, J.dtype, row + x);
     }
   }
+  stage_twiddles_wait();
   __syncthreads();
   if (threadIdx.x < TR * N2) {
     const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
@@ -306,7 +324,7 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
   __shared__ float2 ex[C * D::EX];
   __shared__ float2 sa[C * D::LP];
   __shared__ float2 tw_s[L];
-  for (int i = threadIdx.x; i < L; i += C * D::G) tw_s[i] = __ldg(&tw[i]);
+  stage_twiddles<L, C * D::G>(tw_s, tw);
   const int k0 = blockIdx.x * C;
   const int c = threadIdx.x % C;
   const int r = threadIdx.x / C;  // n2 in pass-1 role, k1 in pass-2 role (r < 16)
@@ -358,6 +376,7 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
       rect = fix3[sl];
       wk = fix3[2];
     }
+    if (sl == 0) stage_twiddles_wait();
     __syncthreads();  // twiddles staged / previous readers of ex done
     if (r < N2) {
       float2 a[kN1];
@@ -449,31 +468,56 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
   __shared__ unsigned long long kred[(NT + 31) / 32];
   const int rp0 = blockIdx.x * TR;
   if (2 * rp0 >= P.sy) return;
-  for (int i = threadIdx.x; i < L; i += NT) tw_s[i] = __ldg(&tw[i]);
   constexpr int NKX = L / 2 + 1;
   const float2* Ub = U + (size_t)blockIdx.z * P.sy * NKX;
-  __syncthreads();
-  if (threadIdx.x < TR * kN1) {  // thread (f, k1)
-    const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
-    const int y = 2 * (rp0 + f);
-    const bool row0 = y < P.sy, row1 = y + 1 < P.sy;
-    const float2* u0p = Ub + (size_t)min(y, P.sy - 1) * NKX;
-    const float2* u1p = Ub + (size_t)min(y + 1, P.sy - 1) * NKX;
-    float2 bq[N2];
+  stage_twiddles<L, NT>(tw_s, tw);  // needed after the first DFT pass
+  const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
+  const int y = 2 * (rp0 + f);
+  const bool line = threadIdx.x < TR * kN1 && y < P.sy;  // thread (f, k1) of a real row
+  float2 bq[N2];
+  if (line) {  // rows past the image: their transform is never read back
+    {
+      const float2* u0p = Ub + (size_t)y * NKX;
+      const float2* u1p = u0p + NKX;
+      // Bin k = k1 + 16 k2 of the Hermitian line: k2 is a compile-time constant after
+      // unrolling, so whole groups of 16 bins are known to lie strictly inside (0, L/2)
+      // (plain load) or strictly above L/2 (mirrored, conjugated load); only the groups
+      // holding the DC or the Nyquist bin need the per-bin tests.
+      auto gather = [&](auto pair_tag) {
+        constexpr bool PAIR = decltype(pair_tag)::value;  // row y + 1 exists
 #pragma unroll
-    for (int k2 = 0; k2 < N2; ++k2) {
-      const int k = k1 + kN1 * k2;
-      const bool mirror = k >= NKX;          // resolved per k2 except for one k2
-      const int kk = mirror ? L - k : k;
-      float2 u0 = __ldg(u0p + kk), u1 = __ldg(u1p + kk);
-      if (!row0) u0 = make_float2(0.f, 0.f);
-      if (!row1) u1 = make_float2(0.f, 0.f);
-      // c2r ignores the imaginary part of the DC and Nyquist bins.
-      if (kk == 0 || kk == L / 2) { u0.y = 0.f; u1.y = 0.f; }
-      if (mirror) { u0.y = -u0.y; u1.y = -u1.y; }
-      bq[k2] = make_float2(u0.y + u1.x, u0.x - u1.y);  // swap_ri(u0 + i u1)
+        for (int k2 = 0; k2 < N2; ++k2) {
+          const int lo = kN1 * k2;
+          const float2 zero = make_float2(0.f, 0.f);
+          if (lo > 0 && lo + kN1 - 1 < L / 2) {
+            const float2 u0 = __ldg(u0p + lo + k1);
+            const float2 u1 = PAIR ? __ldg(u1p + lo + k1) : zero;
+            bq[k2] = make_float2(u0.y + u1.x, u0.x - u1.y);  // swap_ri(u0 + i u1)
+          } else if (lo > L / 2) {
+            const int kk = L - lo - k1;
+            const float2 u0 = __ldg(u0p + kk);
+            const float2 u1 = PAIR ? __ldg(u1p + kk) : zero;
+            bq[k2] = make_float2(-u0.y + u1.x, u0.x + u1.y);  // conjugated bins
+          } else {
+            const int k = lo + k1;
+            const bool mirror = k >= NKX;
+            const int kk = mirror ? L - k : k;
+            float2 u0 = __ldg(u0p + kk);
+            float2 u1 = PAIR ? __ldg(u1p + kk) : zero;
+            // c2r ignores the imaginary part of the DC and Nyquist bins.
+            if (kk == 0 || kk == L / 2) { u0.y = 0.f; u1.y = 0.f; }
+            if (mirror) { u0.y = -u0.y; u1.y = -u1.y; }
+            bq[k2] = make_float2(u0.y + u1.x, u0.x - u1.y);
+          }
+        }
+      };
+      if (y + 1 < P.sy) gather(std::true_type{}); else gather(std::false_type{});
     }
-    Dft<N2>::run(bq);
+  }
+  if (line) Dft<N2>::run(bq);
+  stage_twiddles_wait();
+  __syncthreads();
+  if (line) {
 #pragma unroll
     for (int n2 = 0; n2 < N2; ++n2)
       ex[f * D::EXR + k1 * D::N2P + n2] = cmul(bq[n2], tw_s[k1 * n2]);
@@ -484,28 +528,37 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
   if (threadIdx.x < TR * N2) {  // thread (f, n2)
     const int f = threadIdx.x / N2, n2 = threadIdx.x - f * N2;
     const int y = 2 * (rp0 + f);
-    float2 a[kN1];
-#pragma unroll
-    for (int k1 = 0; k1 < kN1; ++k1) a[k1] = ex[f * D::EXR + k1 * D::N2P + n2];
-    Dft<kN1>::run(a);
     if (y < P.sy) {
-      float* out = images + (size_t)(P.b0 + blockIdx.z) * P.sy * P.sx;
+      float2 a[kN1];
+#pragma unroll
+      for (int k1 = 0; k1 < kN1; ++k1) a[k1] = ex[f * D::EXR + k1 * D::N2P + n2];
+      Dft<kN1>::run(a);
+      const bool pair = y + 1 < P.sy;
+      float* out0 = images + ((size_t)(P.b0 + blockIdx.z) * P.sy + y) * P.sx + n2;
+      float* out1 = out0 + P.sx;
+      // Running maximum per output row with a strict compare in increasing x (keeps the
+      // first of equal values); the 64-bit order-preserving key is built once per row.
+      float bv0 = -INFINITY, bv1 = -INFINITY;
+      int bx0 = n2, bx1 = n2;
+      bool nan0 = false, nan1 = false;
 #pragma unroll
       for (int n1 = 0; n1 < kN1; ++n1) {
         const int x = N2 * n1 + n2;
         if (x >= P.sx) continue;
         // after the re/im swap: real part -> row y, imaginary part -> row y + 1
         const float v0 = a[n1].y * scale, v1 = a[n1].x * scale;
-        out[(size_t)y * P.sx + x] = v0;
-        if (v0 != v0) has_nan = 1;
-        unsigned long long kk = peak_key(v0, (unsigned)(y * P.sx + x));
-        best = kk > best ? kk : best;
-        if (y + 1 < P.sy) {
-          out[(size_t)(y + 1) * P.sx + x] = v1;
-          if (v1 != v1) has_nan = 1;
-          kk = peak_key(v1, (unsigned)((y + 1) * P.sx + x));
-          best = kk > best ? kk : best;
-        }
+        out0[N2 * n1] = v0;
+        if (pair) out1[N2 * n1] = v1;
+        nan0 |= v0 != v0;
+        nan1 |= v1 != v1;
+        if (v0 > bv0) { bv0 = v0; bx0 = x; }
+        if (v1 > bv1) { bv1 = v1; bx1 = x; }
+      }
+      has_nan = (nan0 || (pair && nan1)) ? 1 : 0;
+      best = peak_key(bv0, (unsigned)(y * P.sx + bx0));
+      if (pair) {
+        const unsigned long long k1key = peak_key(bv1, (unsigned)((y + 1) * P.sx + bx1));
+        best = k1key > best ? k1key : best;
       }
     }
   }
