@@ -17,10 +17,12 @@ There is no CPU path here.
 
 from __future__ import annotations
 
+import collections
 import collections.abc
 import os
 import ctypes
 import logging
+import threading
 from typing import Callable, Iterator, Sequence, TypeVar
 
 import numpy as np
@@ -356,9 +358,9 @@ class JAXMaskedXCorrWithStatsCalculator:
     post_d = _device_image(post_image, ctx)
     pre_m = _device_mask(pre_mask, ctx)
     post_m = _device_mask(post_mask, ctx)
-    job = _FlowJob(ctx, oyx, pre_image.shape, post_image.shape, patch_size,
-                   post_patch_size, step, batch_size, pre_targeting_field,
-                   pre_targeting_step, post_targeting_field, post_targeting_step)
+    job = _cached_job(ctx, oyx, pre_image.shape, post_image.shape, patch_size,
+                      post_patch_size, step, batch_size, pre_targeting_field,
+                      pre_targeting_step, post_targeting_field, post_targeting_step)
     peaks_d = job.run(pre_d, post_d, pre_m, post_m, self._mean, self._min_distance,
                       self._peak_radius, progress_fn)
     job.scatter(peaks_d.cpu().numpy(), output)
@@ -480,6 +482,38 @@ class _FlowJob:
       if self.po_all[i] is not None:
         v[:, :nd] = v[:, :nd] - self.po_all[i][:real, ::-1]  # xy[z]
       output[(slice(None),) + tuple(pos_zyx.T)] = v.T
+
+
+# Index tables of recent calls.  A pipeline calls flow_field with the same geometry for
+# every section / tile pair (processor/flow.py:163-251), and building + uploading the
+# tables costs about as much host time as the H2D copy of the images.  Calls with
+# targeting fields (data-dependent starts) are not cached.
+_JOB_CACHE: 'collections.OrderedDict[tuple, _FlowJob]' = collections.OrderedDict()
+_JOB_CACHE_LOCK = threading.Lock()
+_JOB_CACHE_SIZE = 8
+
+
+def _cached_job(ctx, oyx, pre_shape, post_shape, patch_size, post_patch_size, step,
+                batch_size, pre_tf, pre_ts, post_tf, post_ts) -> _FlowJob:
+  if pre_tf is not None or post_tf is not None:
+    return _FlowJob(ctx, oyx, pre_shape, post_shape, patch_size, post_patch_size, step,
+                    batch_size, pre_tf, pre_ts, post_tf, post_ts)
+  key = (ctx.device, tuple(pre_shape), tuple(post_shape), tuple(patch_size),
+         tuple(post_patch_size), tuple(step), int(batch_size), oyx.shape,
+         hash(np.ascontiguousarray(oyx).tobytes()))
+  with _JOB_CACHE_LOCK:
+    job = _JOB_CACHE.get(key)
+    if job is not None and np.array_equal(job.oyx, oyx):
+      _JOB_CACHE.move_to_end(key)
+      return job
+  job = _FlowJob(ctx, oyx, pre_shape, post_shape, patch_size, post_patch_size, step,
+                 batch_size)
+  job.oyx = oyx.copy()
+  with _JOB_CACHE_LOCK:
+    _JOB_CACHE[key] = job
+    while len(_JOB_CACHE) > _JOB_CACHE_SIZE:
+      _JOB_CACHE.popitem(last=False)
+  return job
 
 
 def _targeting_offsets(field, tg_step, starts, patch, img_shape):

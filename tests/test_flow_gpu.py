@@ -311,3 +311,29 @@ def test_shared_row_spectra_match_plain_path(ff, monkeypatch, dtype, post_patch,
   want = fo.MaskedXCorrWithStatsCalculator(mean=mean).flow_field(pre, post, **kw)
   _check_flow(shared, want)
   assert np.isfinite(shared[0]).mean() > 0.9
+
+
+def test_index_tables_are_reused_between_calls(ff):
+  """Same geometry -> the cached index tables; another selection mask -> new tables; the
+  results do not depend on which one was used."""
+  rng = np.random.default_rng(11)
+  base = ndi.gaussian_filter(rng.standard_normal((400, 400)), 2.0)
+  img = ((base - base.min()) / np.ptp(base) * 255).astype(np.uint8)
+  pre, post = img[20:340, 20:340], img[23:343, 18:338]
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  ff._JOB_CACHE.clear()
+  kw = dict(patch_size=160, step=40, batch_size=8)
+  a = calc.flow_field(pre, post, **kw)
+  assert len(ff._JOB_CACHE) == 1
+  job = next(iter(ff._JOB_CACHE.values()))
+  b = calc.flow_field(pre, post, **kw)
+  assert len(ff._JOB_CACHE) == 1 and next(iter(ff._JOB_CACHE.values())) is job
+  np.testing.assert_array_equal(a, b)
+  sel = np.ones(a.shape[1:], bool)
+  sel[1, 2] = False
+  c = calc.flow_field(pre, post, selection_mask=sel, **kw)
+  assert len(ff._JOB_CACHE) == 2
+  assert np.all(np.isnan(c[:, 1, 2]))
+  np.testing.assert_array_equal(c[:2][:, sel], a[:2][:, sel])
+  want = fo.MaskedXCorrWithStatsCalculator().flow_field(pre, post, **kw)
+  _check_flow(a, want)

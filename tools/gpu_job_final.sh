@@ -8,6 +8,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -2 gpurun_out/bench.err
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+timeout 100 python tools/e2e_breakdown.py > gpurun_out/e2e_breakdown.json 2> gpurun_out/e2e_breakdown.err; cat gpurun_out/e2e_breakdown.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --mesh-iters 50 --no-cpu-baseline > gpurun_out/b_under_ncu.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:mesh2d -s 20 -c 2 -f -o gpurun_out/prof_mesh python tools/prof_target.py mesh > gpurun_out/ncu_mesh.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'cols_fast|rows_inv_fast' -s 4 -c 2 -f -o gpurun_out/prof_flow_final python tools/prof_target.py flow > gpurun_out/ncu_flow_final.log 2>&1
 cut -c1-300 gpurun_out/bench.json
