@@ -426,7 +426,49 @@ def stitch_cases(mu, se):
   return out
 
 
+def flow3d_cases(se):
+  """stitch_elastic.compute_flow_map3d (stitch_elastic.py:84-193), the fine-flow step of
+  notebooks/liconn_inplane_stitching.ipynb: 2 x 2 tiles of [1, 24, 56, 64] voxels cut from
+  one 3-d texture with a jittered nominal grid, 3-d patches."""
+  out = {}
+  rng = np.random.default_rng(31)
+  vol = ndi.gaussian_filter(rng.standard_normal((40, 120, 140)), (1.0, 1.5, 1.5))
+  vol = ((vol - vol.min()) / (vol.max() - vol.min()) * 255).astype(np.uint8)
+  tz, th, tw = 24, 56, 64
+  # nominal (z0, y0, x0) of tile (tx, ty): ~25 % overlap plus jitter in all three axes
+  nominal = {(0, 0): (6, 4, 5), (1, 0): (8, 7, 5 + 46), (0, 1): (5, 4 + 41, 8),
+             (1, 1): (7, 6 + 41, 4 + 47)}
+  tiles = {k: np.ascontiguousarray(vol[z0:z0 + tz, y0:y0 + th, x0:x0 + tw])[None]
+           for k, (z0, y0, x0) in nominal.items()}
+  cxm = np.full((3, 1, 2, 2), np.nan)
+  cym = np.full((3, 1, 2, 2), np.nan)
+  for (tx, ty), (z0, y0, x0) in nominal.items():
+    if (tx + 1, ty) in nominal:
+      z1, y1, x1 = nominal[tx + 1, ty]
+      cxm[:, 0, ty, tx] = (x1 - x0 - tw, y1 - y0, z1 - z0)
+    if (tx, ty + 1) in nominal:
+      z1, y1, x1 = nominal[tx, ty + 1]
+      cym[:, 0, ty, tx] = (x1 - x0, y1 - y0 - th, z1 - z0)
+  out['fm3_vol'] = vol
+  out['fm3_nominal'] = np.array([[tx, ty, z0, y0, x0] for (tx, ty), (z0, y0, x0) in nominal.items()])
+  out['fm3_tile_zyx'] = np.array([tz, th, tw])
+  out['fm3_cx'], out['fm3_cy'] = cxm, cym
+  for axis, cm in ((0, cxm), (1, cym)):
+    fl, of = se.compute_flow_map3d(tiles, (tw, th, tz), cm, axis, patch_size=(12, 16, 16),
+                                   stride=(4, 8, 8), batch_size=16)
+    for k in fl:
+      out[f'fm3_flow{axis}_{k[0]}_{k[1]}'] = np.asarray(fl[k])
+      out[f'fm3_off{axis}_{k[0]}_{k[1]}'] = np.array(of[k])
+  return out
+
+
 def main():
+  if 'flow3d' in sys.argv[1:]:
+    se = shim.load_reference('stitch_elastic')
+    path = os.path.join(HERE, 'flow3d_golden.npz')
+    np.savez_compressed(path, **flow3d_cases(se))
+    print('flow3d_golden.npz', os.path.getsize(path) // 1024, 'KiB')
+    return
   if 'stitch' in sys.argv[1:] or len(sys.argv) == 1:
     mu = shim.load_reference('map_utils')
     se = shim.load_reference('stitch_elastic')

@@ -175,3 +175,36 @@ def test_compute_coarse_offsets_host_logic(g, monkeypatch):
   monkeypatch.setattr(flow_field, 'JAXMaskedXCorrWithStatsCalculator',
                       flow_oracle.MaskedXCorrWithStatsCalculator)
   _check_coarse_offsets(g, stitch_rigid)
+
+
+GOLDEN3D = os.path.join(os.path.dirname(__file__), 'golden', 'flow3d_golden.npz')
+
+
+def _check_flow_maps3d(stitch_elastic):
+  """stitch_elastic.compute_flow_map3d (stitch_elastic.py:84-193, the fine-flow step of
+  notebooks/liconn_inplane_stitching.ipynb) against the reference's own run on 2 x 2
+  three-dimensional tiles (tests/golden/make_golden.py flow3d)."""
+  g = np.load(GOLDEN3D)
+  vol = g['fm3_vol']
+  tz, th, tw = (int(v) for v in g['fm3_tile_zyx'])
+  tiles = {(int(a), int(b)): np.ascontiguousarray(vol[z0:z0 + tz, y0:y0 + th, x0:x0 + tw])[None]
+           for a, b, z0, y0, x0 in g['fm3_nominal']}
+  for axis, cm in ((0, g['fm3_cx']), (1, g['fm3_cy'])):
+    flows, offsets = stitch_elastic.compute_flow_map3d(
+        tiles, (tw, th, tz), cm, axis, patch_size=(12, 16, 16), stride=(4, 8, 8), batch_size=16)
+    assert len(flows) == len([k for k in g.files if k.startswith(f'fm3_flow{axis}_')]) == 2
+    for k, f in flows.items():
+      want = g[f'fm3_flow{axis}_{k[0]}_{k[1]}']
+      assert tuple(offsets[k]) == tuple(g[f'fm3_off{axis}_{k[0]}_{k[1]}'])
+      assert f.shape == want.shape
+      np.testing.assert_array_equal(np.isnan(f), np.isnan(want))
+      np.testing.assert_array_equal(f[:3], want[:3])
+      np.testing.assert_allclose(f[3:], want[3:], rtol=2e-3, atol=1e-6)
+
+
+def test_compute_flow_map3d_host_logic(monkeypatch):
+  from oracle import flow_oracle
+  from sofima_b200 import flow_field, stitch_elastic
+  monkeypatch.setattr(flow_field, 'JAXMaskedXCorrWithStatsCalculator',
+                      flow_oracle.MaskedXCorrWithStatsCalculator)
+  _check_flow_maps3d(stitch_elastic)

@@ -232,6 +232,13 @@ def test_compute_flow_map_golden(mods, g):
   _check_flow_maps(g, mods[2])
 
 
+def test_compute_flow_map3d_golden(mods):
+  """stitch_elastic.compute_flow_map3d (LICONN fine flow, 3-d patches) on the CUDA flow
+  path vs the reference's own run (tests/golden/flow3d_golden.npz)."""
+  from tests.test_oracle_stitch import _check_flow_maps3d
+  _check_flow_maps3d(mods[2])
+
+
 def test_config2_pipeline_vs_oracle(mods, g, monkeypatch):
   """BASELINE config 2 in small: fine flow on the overlap strips -> aggregate_arrays ->
   relaxation with the stitching prev_fn, CUDA vs the same pipeline on the oracle."""
