@@ -163,43 +163,50 @@ def masked_xcorr(prev, curr, prev_mask=None, curr_mask=None, use_jax: bool = Fal
                  dim: int = 2):
   """Cross-correlation between two (batches of) masked images (flow_field.py:36).
 
-  Correlation is computed over the last `dim` axes; leading axes are batch.  The
-  inputs are whole patches (no mean subtraction is applied here, as in the
-  reference).  `use_jax` is accepted for signature compatibility.
+  Correlation is computed over the last `dim` axes (2 or 3); leading axes are batch.
+  The inputs are whole patches (no mean subtraction is applied here, as in the
+  reference); `prev` and `curr` may differ in size (the coarse 3-d offset search of
+  notebooks/liconn_inplane_stitching.ipynb correlates a small query cuboid with a
+  large search volume).  `use_jax` is accepted for signature compatibility.
   """
   del use_jax
   prev = np.asarray(prev, dtype=np.float32)
   curr = np.asarray(curr, dtype=np.float32)
-  if dim != 2:
-    raise NotImplementedError('3-d correlation is not part of the CUDA backend yet')
+  if dim not in (2, 3):
+    raise NotImplementedError(f'correlation over {dim} axes: only 2 and 3 are built')
+  if dim == 3 and (prev_mask is not None or curr_mask is not None):
+    raise NotImplementedError('masked 3-d correlation is not part of the CUDA backend yet')
   lead = prev.shape[:-dim]
   pb = prev.reshape((-1,) + prev.shape[-dim:])
   cb = curr.reshape((-1,) + curr.shape[-dim:])
   nb = pb.shape[0]
+  assert cb.shape[0] == nb
   pm = None if prev_mask is None else np.asarray(prev_mask, bool).reshape(pb.shape)
   cm = None if curr_mask is None else np.asarray(curr_mask, bool).reshape(cb.shape)
   ctx = _native.Context.get()
   torch = _torch()
   dev = torch.device('cuda', ctx.device)
-  # Lay the batch out as one tall image so that patch b starts at row b * h.
-  pre = torch.from_numpy(np.ascontiguousarray(pb.reshape(-1, pb.shape[-1]))).to(dev)
-  post = torch.from_numpy(np.ascontiguousarray(cb.reshape(-1, cb.shape[-1]))).to(dev)
-  pre_m = None if pm is None else _device_mask(pm.reshape(-1, pm.shape[-1]), ctx)
-  post_m = None if cm is None else _device_mask(cm.reshape(-1, cm.shape[-1]), ctx)
-  p, pre, post = _params(2, pre, post, pre_m, post_m, pb.shape[1:], cb.shape[1:],
+  # Lay the batch out as one tall image / volume so that patch b starts at b * size[0]
+  # along the first spatial axis.
+  tall = lambda a: np.ascontiguousarray(a.reshape((-1,) + a.shape[2:]))
+  pre = torch.from_numpy(tall(pb)).to(dev)
+  post = torch.from_numpy(tall(cb)).to(dev)
+  pre_m = None if pm is None else _device_mask(tall(pm), ctx)
+  post_m = None if cm is None else _device_mask(tall(cm), ctx)
+  p, pre, post = _params(dim, pre, post, pre_m, post_m, pb.shape[1:], cb.shape[1:],
                          0.0, 2, 0.5, 0)
-  st = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
+  st = torch.zeros((nb, dim), dtype=torch.int32, device=dev)
   st[:, 0] = torch.arange(nb, device=dev, dtype=torch.int32) * pb.shape[1]
-  pst = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
+  pst = torch.zeros((nb, dim), dtype=torch.int32, device=dev)
   pst[:, 0] = torch.arange(nb, device=dev, dtype=torch.int32) * cb.shape[1]
-  sy, sx = pb.shape[1] + cb.shape[1] - 1, pb.shape[2] + cb.shape[2] - 1
-  out = torch.empty((nb, sy, sx), dtype=torch.float32, device=dev)
+  out_shape = tuple(int(a) + int(b) - 1 for a, b in zip(pb.shape[1:], cb.shape[1:]))
+  out = torch.empty((nb,) + out_shape, dtype=torch.float32, device=dev)
   ctx.bind_stream()
   rc = _native.lib().sofima_xcorr_images(
       ctx.handle, ctypes.byref(p), pre.data_ptr(), post.data_ptr(), _ptr(pre_m),
       _ptr(post_m), st.data_ptr(), pst.data_ptr(), nb, out.data_ptr())
   _native.check(ctx.handle, rc)
-  return out.cpu().numpy().reshape(lead + (sy, sx))
+  return out.cpu().numpy().reshape(lead + out_shape)
 
 
 def _batched_peaks(img, center_offset, min_distance, threshold_rel,

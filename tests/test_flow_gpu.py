@@ -337,3 +337,32 @@ def test_index_tables_are_reused_between_calls(ff):
   np.testing.assert_array_equal(c[:2][:, sel], a[:2][:, sel])
   want = fo.MaskedXCorrWithStatsCalculator().flow_field(pre, post, **kw)
   _check_flow(a, want)
+
+
+def test_masked_xcorr_3d_unequal_volumes(ff):
+  """flow_field.masked_xcorr(dim=3) + _batched_peaks as the coarse 3-d offset search of
+  notebooks/liconn_inplane_stitching.ipynb (cell 12) uses them: a small query cuboid
+  correlated with a larger search volume, no masks, peak relative to a caller-supplied
+  centre."""
+  rng = np.random.default_rng(21)
+  vol = ndi.gaussian_filter(rng.standard_normal((40, 44, 48)), 1.2).astype(np.float32)
+  search = vol[4:34, 6:38, 2:42]                      # 30 x 32 x 40
+  query = vol[4 + 9:4 + 9 + 8, 6 + 11:6 + 11 + 10, 2 + 13:2 + 13 + 12].copy()   # at (9, 11, 13)
+  search = search - search.mean()
+  query = query - query.mean()
+  got = ff.masked_xcorr(search, query, use_jax=True, dim=3)
+  want = fo.masked_xcorr(search, query, dim=3)
+  assert got.shape == want.shape == (37, 41, 51)
+  scale = np.abs(want).max()
+  np.testing.assert_allclose(got / scale, want / scale, atol=3e-6)
+  center = (got.shape[0] // 2, got.shape[1] // 2, got.shape[2] // 2)
+  pk = ff._batched_peaks(got[None], center, 2, 0.5)
+  pk_w = fo.batched_peaks(want[None], center, 2, 0.5)
+  np.testing.assert_array_equal(pk[0, :3], pk_w[0, :3])
+  np.testing.assert_allclose(pk[0, 3:], pk_w[0, 3:], rtol=2e-3, atol=1e-6)
+  # batch axis + the error contract
+  b2 = ff.masked_xcorr(np.stack([search, search]), np.stack([query, -query]), dim=3)
+  np.testing.assert_allclose(b2[0] / scale, want / scale, atol=3e-6)
+  np.testing.assert_allclose(b2[1] / scale, -want / scale, atol=3e-6)
+  with pytest.raises(NotImplementedError):
+    ff.masked_xcorr(search, query, np.zeros(search.shape, bool), None, dim=3)
