@@ -16,8 +16,10 @@ from typing import Sequence
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, '_lib')
-# SOFIMA_B200_LIB: load another build of the same C ABI (kernel A/B measurements).
-LIB_PATH = os.environ.get('SOFIMA_B200_LIB') or os.path.join(LIB_DIR, 'libsofima_b200.so')
+BUILD_LIB_PATH = os.path.join(LIB_DIR, 'libsofima_b200.so')  # what build() writes
+# SOFIMA_B200_LIB: load another build of the same C ABI (kernel A/B measurements,
+# tools/ab_flow.py); build() never writes there.
+LIB_PATH = os.environ.get('SOFIMA_B200_LIB') or BUILD_LIB_PATH
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC_ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
@@ -76,14 +78,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     out, _ = proc.communicate()
     if proc.returncode != 0:
       raise NativeError('nvcc failed: %s\n%s' % (' '.join(cmd), out.decode()))
-  if force or procs or _stale(LIB_PATH, objs):
-    cmd = [_nvcc()] + NVCC_ARCH + ['-shared', '-o', LIB_PATH] + objs
+  if force or procs or _stale(BUILD_LIB_PATH, objs):
+    cmd = [_nvcc()] + NVCC_ARCH + ['-shared', '-o', BUILD_LIB_PATH] + objs
     if verbose:
       print(' '.join(cmd))
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if res.returncode != 0:
       raise NativeError('link failed: %s\n%s' % (' '.join(cmd), res.stdout.decode()))
-  return LIB_PATH
+  return BUILD_LIB_PATH
 
 
 # --- ctypes mirror of include/sofima_b200.h ---------------------------------------
