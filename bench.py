@@ -55,12 +55,38 @@ def _traffic(kernel):
 
 def _peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-  if os.path.exists(path):
+  try:
     d = json.load(open(path))
-    return dict(hbm_gbs=d['hbm_gbs'], tflops=d['bf16_tflops_sustained'],
+    return dict(hbm_gbs=float(d['hbm_gbs']), tflops=float(d['bf16_tflops_sustained']),
                 source='measured (MEASURED_PEAKS.json)')
-  return dict(hbm_gbs=6650.0, tflops=1590.0,
-              source='fallback (B200_PROFILING.md)')
+  except (OSError, KeyError, ValueError, TypeError):
+    return dict(hbm_gbs=6650.0, tflops=1590.0,
+                source='fallback (B200_PROFILING.md)')
+
+
+def flow_kernel_rooflines(kern_ms, pairs, tile, patch, step, hbm_gbs):
+  """HBM view of the flow kernels of one step: algorithmic bytes
+  of each stage (what it has to read and write once, per patch pair or per tile pair)
+  over its measured device time.  kern_ms: {timer name: ms per step}."""
+  l = 2 * patch - 1                      # correlation image edge (319)
+  nkx = (l + 1) // 2 + 1                 # half-spectrum bins of the 320-point rows (161)
+  spec = l * nkx * 8                     # product spectra of one pair, complex64
+  image = l * l * 4                      # correlation image of one pair, fp32
+  rows = 2 * patch * nkx * 8             # cached row spectra one pair reads (both patches)
+  nx = (tile - (patch - step)) // step   # distinct patch x starts (99)
+  alg = {
+      'flow_cols': pairs * (rows + spec),
+      'flow_rows_inv': pairs * (spec + image),
+      'flow_rowspec': 2 * (tile * tile + nx * tile * nkx * 8),
+  }
+  out = {}
+  for name, nbytes in alg.items():
+    ms = kern_ms.get(name)
+    if ms:
+      gbs = nbytes / (ms * 1e-3) / 1e9
+      out[name] = {'bound': 'hbm', 'algorithmic_bytes_per_step': int(nbytes),
+                   'achieved': gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': gbs / hbm_gbs}
+  return out
 
 
 # ----------------------------------------------------------------------------------
@@ -466,7 +492,9 @@ def run_ours(args):
                     'the summed device time of the flow kernels of one step; the work '
                     'is executed as fp32 FFTs on the CUDA cores (~13 MFLOP/pair), '
                     'see DESIGN.md',
-            'dominant_kernel': dom, 'kernel_ms_per_step': kern_ms},
+            'dominant_kernel': dom, 'kernel_ms_per_step': kern_ms,
+            'kernels_hbm_view': flow_kernel_rooflines(kern_ms, pairs_per_step, FLOW_TILE,
+                                                      PATCH, STEP, peaks['hbm_gbs'])},
         'e2e': {'value': world * pairs_per_step * K / (e2e_ms * 1e-3),
                 'unit': 'patch-pairs/s',
                 'h2d_bytes_per_step': 2 * FLOW_TILE * FLOW_TILE + int(job.starts_d.numel()) * 4,
