@@ -220,3 +220,78 @@ def target_mesh_all(nbors, x, fx, fy, stride):
   [dim, n, ...] (notebooks/em_stitching.ipynb:545-549)."""
   out = np.stack([compute_target_mesh(nd, x, fx, fy, stride) for nd in nbors])
   return np.moveaxis(out, 0, 1)
+
+
+# ------------------------------------------------------------------------------------
+# Rigid tile-grid step (stitch_rigid.py:277-545): every tile is one node of a small mesh
+# whose springs want the measured coarse offsets between neighbouring tiles.
+# ------------------------------------------------------------------------------------
+def _tile_links(x, cx, cy, terms):
+  """Sum of the spring terms of stitch_rigid.elastic_tile_mesh[_3d] in the reference's
+  order.  A term (comp, axis, target) is: f = nan_to_num(x[comp, next] - x[comp, this] -
+  target), added to `this` and subtracted from `next` along `axis` (-1: x neighbour,
+  -2: y neighbour); the reference adds zero-padded copies of f to the whole array."""
+  x = np.asarray(x, dtype=F32)
+  tgt = {'cx': np.asarray(cx, dtype=F32), 'cy': np.asarray(cy, dtype=F32)}
+  f_tot = np.zeros_like(x)
+  for comp, axis, which in terms:
+    this = [slice(None)] * 3
+    nxt = [slice(None)] * 3
+    this[axis] = slice(None, -1)
+    nxt[axis] = slice(1, None)
+    this, nxt = tuple(this), tuple(nxt)
+    d = x[comp][nxt] - x[comp][this]
+    f = np.nan_to_num(d - tgt[which][comp][this]).astype(F32)
+    f_tot[comp][this] = f_tot[comp][this] + f
+    f_tot[comp][nxt] = f_tot[comp][nxt] - f
+  return f_tot
+
+
+def elastic_tile_mesh(x, cx, cy, k=None, stride=None, prefer_orig_order=False, links=None):
+  """stitch_rigid.elastic_tile_mesh (stitch_rigid.py:330-391); x: [2, z, y, x]."""
+  del k, stride, prefer_orig_order, links
+  return _tile_links(x, cx, cy, ((0, -1, 'cx'), (1, -2, 'cy'), (0, -2, 'cy'), (1, -1, 'cx')))
+
+
+def elastic_tile_mesh_3d(x, cx, cy, k=None, stride=None, prefer_orig_order=False, links=None):
+  """stitch_rigid.elastic_tile_mesh_3d (stitch_rigid.py:394-473); x: [3, z, y, x]."""
+  del k, stride, prefer_orig_order, links
+  return _tile_links(x, cx, cy, ((0, -1, 'cx'), (1, -2, 'cy'), (0, -2, 'cy'), (1, -1, 'cx'),
+                                 (2, -1, 'cx'), (2, -2, 'cy')))
+
+
+def optimize_coarse_mesh(cx, cy, cfg=None, mesh_fn=elastic_tile_mesh):
+  """stitch_rigid.optimize_coarse_mesh (stitch_rigid.py:476-545): relaxes the all-zero tile
+  mesh under `mesh_fn`; returns the tile positions relative to the regular grid."""
+  from oracle import mesh_oracle
+  if cfg is None:
+    from sofima_b200.mesh import IntegrationConfig  # the dataclass only
+    cfg = IntegrationConfig(dt=0.001, gamma=0.0, k0=0.0, k=0.1, stride=(1, 1),
+                            num_iters=1000, max_iters=100000, stop_v_max=0.001, dt_max=100)
+  force = lambda x, k, stride, prefer_orig_order=False: mesh_fn(x, cx, cy)
+  res = mesh_oracle.relax_mesh(np.zeros(np.shape(cx), F32), None, cfg, mesh_force=force)
+  return np.array(res[0])
+
+
+def interpolate_missing_offsets(conn, axis, max_r=4):
+  """stitch_rigid.interpolate_missing_offsets (stitch_rigid.py:277-327): an offset marked
+  inf is replaced by the mean of its nearest finite neighbours at the smallest distance
+  1 <= r < max_r along `axis` (-1: x, -2: y); in place, returns conn."""
+  if conn.ndim != 4:
+    raise ValueError('conn array must have rank 4')
+  n = conn.shape[axis]
+  for y, x in zip(*np.where(np.isinf(conn[0, 0]))):
+    pos = (y, x)[axis + 2]
+    for r in range(1, max_r):
+      found = []
+      for q in (pos - r, pos + r):
+        if 0 <= q < n:
+          idx = [0, 0, y, x]
+          idx[axis] = q
+          if np.isfinite(conn[tuple(idx)]):
+            idx[0] = slice(None)
+            found.append(conn[tuple(idx)])
+      if found:
+        conn[:, 0, y, x] = np.mean(found, axis=0)
+        break
+  return conn

@@ -3,14 +3,17 @@ stitch_rigid.py):
 
   _estimate_offset[_horiz|_vert]   stitch_rigid.py:39-101
   compute_coarse_offsets           stitch_rigid.py:104-273
+  interpolate_missing_offsets      stitch_rigid.py:277-327 (host NumPy, as upstream)
 
 The offset between two neighbouring tiles is the peak of ONE masked normalised
 cross-correlation of their whole overlap strips (e.g. 4096 x 300 px -> 8192 x 600-point
 transforms), computed by the CUDA flow path (long-column form of csrc/flow.cu).  The
 low-contrast masks are SciPy min / max filters on the host, as in the reference.  The
-rigid mesh optimisation on top of the offsets (`optimize_coarse_mesh`,
-stitch_rigid.py:386-545) relaxes a 3 x 3-node-per-tile system with a custom force and
-is not part of this backend.
+rigid mesh optimisation on top of the offsets (`optimize_coarse_mesh` with
+`elastic_tile_mesh[_3d]`, stitch_rigid.py:330-545) relaxes a one-node-per-tile mesh with
+its own linear spring force; its oracle is pinned on the reference's run
+(oracle/stitch_oracle.py, tests/golden/coarse_golden.npz) but the device kernel is not
+built yet, so the function raises NotImplementedError here.
 """
 
 from __future__ import annotations
@@ -141,3 +144,51 @@ def compute_coarse_offsets(yx_shape: tuple[int, int],
                                        tile_map[x, y + 1], overlaps_xy[1],
                                        max(overlaps_xy[0]), 1, masks)
   return conn_x, conn_y
+
+
+def interpolate_missing_offsets(conn: np.ndarray, axis: int, max_r: int = 4) -> np.ndarray:
+  """Estimates missing coarse offsets (stitch_rigid.py:277-327).
+
+  Offsets marked inf ("no acceptable estimate") are replaced by the mean of the finite
+  offsets found at the smallest distance 1 <= r < max_r on either side along `axis`.
+
+  Args:
+    conn: [2 or 3, 1, y, x] coarse offsets as returned by compute_coarse_offsets;
+      modified in place
+    axis: axis of `conn` along which neighbours are searched (-1: x, -2: y)
+    max_r: search radius (exclusive)
+
+  Returns:
+    conn; still inf where no finite neighbour lies within the radius
+  """
+  if conn.ndim != 4:
+    raise ValueError('conn array must have rank 4')
+  length = conn.shape[axis]
+  for y, x in zip(*np.where(np.isinf(conn[0, 0, ...]))):
+    centre = (y, x)[axis + 2]
+    for r in range(1, max_r):
+      hits = []
+      for q in (centre - r, centre + r):
+        if not 0 <= q < length:
+          continue
+        where = [0, 0, y, x]
+        where[axis] = q
+        if np.isfinite(conn[tuple(where)]):
+          where[0] = slice(None)
+          hits.append(conn[tuple(where)])
+      if hits:
+        conn[:, 0, y, x] = np.mean(hits, axis=0)
+        break
+  return conn
+
+
+def optimize_coarse_mesh(cx, cy, cfg=None, mesh_fn=None):
+  """Rough initial tile positions from the coarse offsets (stitch_rigid.py:476-545).
+
+  Not built on the device yet: the one-node-per-tile relaxation uses its own force
+  field (`elastic_tile_mesh[_3d]`), which the mesh kernels do not evaluate.
+  """
+  del cx, cy, cfg, mesh_fn
+  raise NotImplementedError(
+      'optimize_coarse_mesh: the tile-grid force field is not part of the CUDA backend yet '
+      '(DESIGN.md section 7)')

@@ -462,7 +462,72 @@ def flow3d_cases(se):
   return out
 
 
+def coarse_cases(sr, mesh):
+  """stitch_rigid.{interpolate_missing_offsets, elastic_tile_mesh[_3d], optimize_coarse_mesh}
+  (stitch_rigid.py:277-545): the rigid tile-grid step between the coarse offsets and the
+  fine flow in both stitching notebooks."""
+  out = {}
+  rng = np.random.default_rng(41)
+  ny, nx = 3, 4
+  # offsets as compute_coarse_offsets returns them: [2, 1, y, x], NaN where there is no
+  # neighbour, a jittered nominal overlap elsewhere
+  cx = np.full((2, 1, ny, nx), np.nan)
+  cy = np.full((2, 1, ny, nx), np.nan)
+  cx[0, 0, :, :-1] = -40 + rng.integers(-6, 7, (ny, nx - 1))
+  cx[1, 0, :, :-1] = rng.integers(-8, 9, (ny, nx - 1))
+  cy[0, 0, :-1, :] = rng.integers(-8, 9, (ny - 1, nx))
+  cy[1, 0, :-1, :] = -30 + rng.integers(-6, 7, (ny - 1, nx))
+  out['cm2_cx'], out['cm2_cy'] = cx, cy
+  x = (rng.standard_normal((2, 1, ny, nx)) * 5).astype(np.float32)
+  out['cm2_x'] = x
+  out['cm2_force'] = np.asarray(sr.elastic_tile_mesh(shim.asjax(x), shim.asjax(cx), shim.asjax(cy)))
+  # The reference starts from np.zeros_like(cx); real JAX (x64 disabled) turns float64 NumPy
+  # inputs into float32 at the jit boundary, the shim would keep them in float64 -- so the
+  # offsets are handed over as float32 here.
+  f32 = lambda a: a.astype(np.float32)
+  out['cm2_opt'] = np.asarray(sr.optimize_coarse_mesh(f32(cx), f32(cy)))
+  cfg = dict(dt=0.001, gamma=0.0, k0=0.0, k=0.1, stride=(1, 1), num_iters=100, max_iters=300,
+             stop_v_max=0.0, dt_max=100)
+  out['cm2_short_cfg'] = np.array(repr(cfg))
+  out['cm2_short'] = np.asarray(sr.optimize_coarse_mesh(f32(cx), f32(cy),
+                                                      cfg=mesh.IntegrationConfig(**cfg)))
+  # 3-d tiles (LICONN): XYZ offsets, elastic_tile_mesh_3d
+  cx3 = np.full((3, 1, ny, nx), np.nan)
+  cy3 = np.full((3, 1, ny, nx), np.nan)
+  cx3[0, 0, :, :-1] = -40 + rng.integers(-6, 7, (ny, nx - 1))
+  cx3[1, 0, :, :-1] = rng.integers(-8, 9, (ny, nx - 1))
+  cx3[2, 0, :, :-1] = rng.integers(-4, 5, (ny, nx - 1))
+  cy3[0, 0, :-1, :] = rng.integers(-8, 9, (ny - 1, nx))
+  cy3[1, 0, :-1, :] = -30 + rng.integers(-6, 7, (ny - 1, nx))
+  cy3[2, 0, :-1, :] = rng.integers(-4, 5, (ny - 1, nx))
+  out['cm3_cx'], out['cm3_cy'] = cx3, cy3
+  x3 = (rng.standard_normal((3, 1, ny, nx)) * 5).astype(np.float32)
+  out['cm3_x'] = x3
+  out['cm3_force'] = np.asarray(sr.elastic_tile_mesh_3d(shim.asjax(x3), shim.asjax(cx3),
+                                                        shim.asjax(cy3)))
+  out['cm3_opt'] = np.asarray(sr.optimize_coarse_mesh(f32(cx3), f32(cy3),
+                                                    mesh_fn=sr.elastic_tile_mesh_3d))
+  # interpolate_missing_offsets: inf = "no acceptable estimate"
+  conn = cx.copy()
+  conn[:, 0, 1, 1] = np.inf
+  conn[:, 0, 0, 0] = np.inf
+  conn[:, 0, 2, 2] = np.inf
+  conn[:, 0, 2, 1] = np.inf
+  out['im_in'] = conn.copy()
+  out['im_x'] = sr.interpolate_missing_offsets(conn.copy(), -1)
+  out['im_y'] = sr.interpolate_missing_offsets(conn.copy(), -2)
+  out['im_y_r2'] = sr.interpolate_missing_offsets(conn.copy(), -2, max_r=2)
+  return out
+
+
 def main():
+  if 'coarse' in sys.argv[1:]:
+    sr = shim.load_reference('stitch_rigid')
+    mesh = shim.load_reference('mesh')
+    path = os.path.join(HERE, 'coarse_golden.npz')
+    np.savez_compressed(path, **coarse_cases(sr, mesh))
+    print('coarse_golden.npz', os.path.getsize(path) // 1024, 'KiB')
+    return
   if 'flow3d' in sys.argv[1:]:
     se = shim.load_reference('stitch_elastic')
     path = os.path.join(HERE, 'flow3d_golden.npz')

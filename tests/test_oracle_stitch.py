@@ -208,3 +208,56 @@ def test_compute_flow_map3d_host_logic(monkeypatch):
   monkeypatch.setattr(flow_field, 'JAXMaskedXCorrWithStatsCalculator',
                       flow_oracle.MaskedXCorrWithStatsCalculator)
   _check_flow_maps3d(stitch_elastic)
+
+
+# ---- rigid tile-grid step (stitch_rigid.py:277-545) ---------------------------------
+COARSE = os.path.join(os.path.dirname(__file__), 'golden', 'coarse_golden.npz')
+
+
+def test_tile_mesh_forces_golden():
+  g = np.load(COARSE)
+  np.testing.assert_array_equal(
+      so.elastic_tile_mesh(g['cm2_x'], g['cm2_cx'], g['cm2_cy']), g['cm2_force'])
+  np.testing.assert_array_equal(
+      so.elastic_tile_mesh_3d(g['cm3_x'], g['cm3_cx'], g['cm3_cy']), g['cm3_force'])
+
+
+def test_optimize_coarse_mesh_golden():
+  # the reference's own optimize_coarse_mesh (default config: FIRE until v_max < 1e-3,
+  # and a fixed 300 steps) on a 3 x 4 tile grid, 2-d and 3-d offsets
+  import ast
+  from sofima_b200.mesh import IntegrationConfig
+  g = np.load(COARSE)
+  cfg = IntegrationConfig(**ast.literal_eval(str(g['cm2_short_cfg'])))
+  np.testing.assert_array_equal(
+      so.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'], cfg), g['cm2_short'])
+  np.testing.assert_array_equal(so.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy']), g['cm2_opt'])
+  np.testing.assert_array_equal(
+      so.optimize_coarse_mesh(g['cm3_cx'], g['cm3_cy'], mesh_fn=so.elastic_tile_mesh_3d),
+      g['cm3_opt'])
+  # the solution realises the requested offsets where the grid is consistent with them
+  opt = g['cm2_opt']
+  dx = opt[0, 0, :, 1:] - opt[0, 0, :, :-1]
+  assert np.abs(dx - g['cm2_cx'][0, 0, :, :-1]).max() < 8.0
+
+
+def test_interpolate_missing_offsets_golden():
+  g = np.load(COARSE)
+  for key, axis, kw in (('im_x', -1, {}), ('im_y', -2, {}), ('im_y_r2', -2, {'max_r': 2})):
+    got = so.interpolate_missing_offsets(g['im_in'].copy(), axis, **kw)
+    np.testing.assert_array_equal(got, g[key])
+  with pytest.raises(ValueError):
+    so.interpolate_missing_offsets(np.zeros((2, 3, 4)), -1)
+
+
+def test_product_interpolate_missing_offsets_golden():
+  # host NumPy in the product too (as in the reference); the relaxation itself is not built
+  from sofima_b200 import stitch_rigid
+  g = np.load(COARSE)
+  for key, axis, kw in (('im_x', -1, {}), ('im_y', -2, {}), ('im_y_r2', -2, {'max_r': 2})):
+    got = stitch_rigid.interpolate_missing_offsets(g['im_in'].copy(), axis, **kw)
+    np.testing.assert_array_equal(got, g[key])
+  with pytest.raises(ValueError):
+    stitch_rigid.interpolate_missing_offsets(np.zeros((2, 3, 4)), -1)
+  with pytest.raises(NotImplementedError):
+    stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'])
