@@ -11,9 +11,9 @@ transforms), computed by the CUDA flow path (long-column form of csrc/flow.cu). 
 low-contrast masks are SciPy min / max filters on the host, as in the reference.  The
 rigid mesh optimisation on top of the offsets (`optimize_coarse_mesh` with
 `elastic_tile_mesh[_3d]`, stitch_rigid.py:330-545) relaxes a one-node-per-tile mesh with
-its own linear spring force; its oracle is pinned on the reference's run
-(oracle/stitch_oracle.py, tests/golden/coarse_golden.npz) but the device kernel is not
-built yet, so the function raises NotImplementedError here.
+its own linear spring force; the CPU restatement used by the tests is pinned on the
+reference's run (tests/golden/coarse_golden.npz) but the device kernel is not built yet,
+so the function raises NotImplementedError here.
 """
 
 from __future__ import annotations
