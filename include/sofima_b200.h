@@ -115,6 +115,25 @@ int sofima_mesh_chunk(sofima_ctx* ctx, int force_kind, float* x, float* v,
                       float* alpha, float* cap, int32_t* n_pos, double* e_kin,
                       float* v_max);
 
+/* Rigid tile-grid step between the coarse offsets and the fine flow of the stitching
+ * notebooks: every tile is one node of a [ncomp][nb * nz][ny][nx] mesh (ncomp = 2: XY,
+ * 3: XYZ offsets), cx / cy are the measured offsets to the +x / +y neighbour in the same
+ * layout (NaN = no neighbour or no estimate).
+ * sofima_tile_mesh_force replaces stitch_rigid.elastic_tile_mesh (stitch_rigid.py:330-391)
+ * and elastic_tile_mesh_3d (:394-473) called on their own. */
+int sofima_tile_mesh_force(sofima_ctx* ctx, const float* x, const float* cx,
+                           const float* cy, const sofima_mesh_shape* shape, float* out);
+
+/* Replaces ONE mesh.velocity_verlet call of stitch_rigid.optimize_coarse_mesh
+ * (stitch_rigid.py:476-545: mesh_force = elastic_tile_mesh[_3d], prev = None) plus the two
+ * reductions of relax_mesh (mesh.py:584-586); arguments as sofima_mesh_chunk.  The whole
+ * chunk runs in one thread block.  cfg->k0, k, stride are unused (as in the reference);
+ * cfg->remove_drift is not supported. */
+int sofima_tile_mesh_chunk(sofima_ctx* ctx, float* x, float* v, float* a, const float* cx,
+                           const float* cy, const sofima_mesh_shape* shape,
+                           const sofima_integration_config* cfg, float* dt, float* alpha,
+                           float* cap, int32_t* n_pos, double* e_kin, float* v_max);
+
 /* Device-side solver state; also the layout of the read-back block. */
 typedef struct {
   float dt, alpha, cap, gate; /* FIRE scalars after the last step; gate = (power >= 0) */

@@ -29,6 +29,7 @@ NVCC_COMMON = ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 SOURCES = {
     'ctx.cu': [],
     'mesh.cu': ['-fmad=false'],
+    'tile_mesh.cu': ['-fmad=false'],  # fp32 operation order of mesh.py / stitch_rigid.py
     'flow.cu': [],
     'warp.cu': ['-fmad=false'],  # float64 arithmetic identical to SciPy's
 }
@@ -168,6 +169,14 @@ _PROTOS = {
         ctypes.POINTER(ctypes.c_float)]),
     'sofima_mesh_chunk_stitch': (ctypes.c_int, [
         _vp, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(StitchTargetPod), ctypes.POINTER(MeshShape),
+        ctypes.POINTER(IntegrationConfigPod), ctypes.POINTER(ctypes.c_float),
+        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
+        ctypes.POINTER(ctypes.c_float)]),
+    'sofima_tile_mesh_force': (ctypes.c_int, [
+        _vp, _vp, _vp, _vp, ctypes.POINTER(MeshShape), _vp]),
+    'sofima_tile_mesh_chunk': (ctypes.c_int, [
+        _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(MeshShape),
         ctypes.POINTER(IntegrationConfigPod), ctypes.POINTER(ctypes.c_float),
         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),

@@ -11,19 +11,22 @@ transforms), computed by the CUDA flow path (long-column form of csrc/flow.cu). 
 low-contrast masks are SciPy min / max filters on the host, as in the reference.  The
 rigid mesh optimisation on top of the offsets (`optimize_coarse_mesh` with
 `elastic_tile_mesh[_3d]`, stitch_rigid.py:330-545) relaxes a one-node-per-tile mesh with
-its own linear spring force; the CPU restatement used by the tests is pinned on the
-reference's run (tests/golden/coarse_golden.npz) but the device kernel is not built yet,
-so the function raises NotImplementedError here.
+its own linear spring force: csrc/tile_mesh.cu runs a whole chunk of integration steps in
+one thread block (`sofima_tile_mesh_chunk`).
 """
 
 from __future__ import annotations
 
+import ctypes
+import dataclasses
 from typing import Mapping, Sequence
 
 import numpy as np
 from scipy import ndimage
 
+from . import _native
 from . import flow_field
+from . import mesh
 
 MaskMap = Mapping[tuple[int, int], np.ndarray]
 
@@ -182,13 +185,131 @@ def interpolate_missing_offsets(conn: np.ndarray, axis: int, max_r: int = 4) -> 
   return conn
 
 
-def optimize_coarse_mesh(cx, cy, cfg=None, mesh_fn=None):
-  """Rough initial tile positions from the coarse offsets (stitch_rigid.py:476-545).
+def _tile_arrays(ctx, *arrays):
+  """fp32 contiguous CUDA copies of [ncomp, z, y, x] arrays of one common shape."""
+  torch = mesh._torch()
+  dev = torch.device('cuda', ctx.device)
+  out = []
+  for a in arrays:
+    if mesh._is_tensor(a):
+      t = a.to(dev, dtype=torch.float32).contiguous()
+    else:
+      t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    out.append(t)
+  shape = tuple(out[0].shape)
+  if len(shape) != 4 or any(tuple(t.shape) != shape for t in out):
+    raise ValueError('x, cx and cy must be [2 or 3, z, y, x] arrays of the same shape')
+  return out
 
-  Not built on the device yet: the one-node-per-tile relaxation uses its own force
-  field (`elastic_tile_mesh[_3d]`), which the mesh kernels do not evaluate.
+
+def _tile_shape(shape, ncomp: int) -> _native.MeshShape:
+  if shape[0] != ncomp:
+    raise ValueError(f'expected {ncomp} components, got an array of shape {shape}')
+  return _native.MeshShape(ncomp, 1, shape[1], shape[2], shape[3], 0)
+
+
+def _tile_force(x, cx, cy, ncomp: int):
+  dev = x.device.index if mesh._is_tensor(x) and x.is_cuda else None
+  ctx = _native.Context.get(dev)
+  xd, cxd, cyd = _tile_arrays(ctx, x, cx, cy)
+  out = mesh._torch().empty_like(xd)
+  shape = _tile_shape(tuple(xd.shape), ncomp)
+  ctx.bind_stream()
+  rc = _native.lib().sofima_tile_mesh_force(ctx.handle, xd.data_ptr(), cxd.data_ptr(),
+                                            cyd.data_ptr(), ctypes.byref(shape),
+                                            out.data_ptr())
+  _native.check(ctx.handle, rc)
+  return out if mesh._is_tensor(x) else out.cpu().numpy()
+
+
+def elastic_tile_mesh(x, cx, cy, k=None, stride=None, prefer_orig_order=False, links=None):
+  """Force on the nodes of a 2-d tile mesh (stitch_rigid.py:330-391).
+
+  Args:
+    x: [2, z, y, x] mesh where every node represents a tile
+    cx: desired XY offsets between (x, y) and (x+1, y) tiles, same shape
+    cy: desired XY offsets between (x, y) and (x, y+1) tiles, same shape
+    k, stride, prefer_orig_order, links: unused (mesh solver compatibility)
+
+  Returns:
+    force field acting on the mesh, same shape as x
   """
-  del cx, cy, cfg, mesh_fn
-  raise NotImplementedError(
-      'optimize_coarse_mesh: the tile-grid force field is not part of the CUDA backend yet '
-      '(DESIGN.md section 7)')
+  del k, stride, prefer_orig_order, links
+  return _tile_force(x, cx, cy, 2)
+
+
+def elastic_tile_mesh_3d(x, cx, cy, k=None, stride=None, prefer_orig_order=False, links=None):
+  """Force on the nodes of a 3-d tile mesh, XYZ offsets (stitch_rigid.py:394-473)."""
+  del k, stride, prefer_orig_order, links
+  return _tile_force(x, cx, cy, 3)
+
+
+def default_coarse_mesh_config() -> mesh.IntegrationConfig:
+  """The settings optimize_coarse_mesh falls back to (stitch_rigid.py:496-507)."""
+  return mesh.IntegrationConfig(dt=0.001, gamma=0.0, k0=0.0, k=0.1, stride=(1, 1),
+                                num_iters=1000, max_iters=100000, stop_v_max=0.001,
+                                dt_max=100)
+
+
+def optimize_coarse_mesh(cx, cy, cfg: mesh.IntegrationConfig | None = None,
+                         mesh_fn=elastic_tile_mesh) -> np.ndarray:
+  """Computes rough initial positions of the tiles (stitch_rigid.py:476-545).
+
+  Args:
+    cx: desired XY[Z] offsets between (x, y) and (x+1, y) tiles, [2 or 3, 1, y, x]
+    cy: desired XY[Z] offsets between (x, y) and (x, y+1) tiles
+    cfg: integration config; None = default_coarse_mesh_config()
+    mesh_fn: `elastic_tile_mesh` or `elastic_tile_mesh_3d` of this module
+
+  Returns:
+    optimized tile positions relative to the regular no-overlap grid, shaped like cx
+  """
+  if mesh_fn is elastic_tile_mesh:
+    ncomp = 2
+  elif mesh_fn is elastic_tile_mesh_3d:
+    ncomp = 3
+  else:
+    raise NotImplementedError(
+        'The CUDA backend runs the built-in tile-mesh force fields only '
+        '(sofima_b200.stitch_rigid.elastic_tile_mesh / elastic_tile_mesh_3d); arbitrary '
+        f'Python callables such as {mesh_fn!r} cannot be traced into the kernel.')
+  if cfg is None:
+    cfg = default_coarse_mesh_config()
+  if cfg.start_cap != cfg.final_cap:  # relax_mesh's own argument checks, mesh.py:556-568
+    if not cfg.fire:
+      raise NotImplementedError('Adaptive force capping is only supported with FIRE.')
+    if cfg.cap_scale <= 1:
+      raise ValueError('The scaling factor for the force cap has to be larger '
+                       'than 1 when the initial and final cap are different.')
+
+  ctx = _native.Context.get()
+  cxd, cyd = _tile_arrays(ctx, cx, cy)
+  torch = mesh._torch()
+  x = torch.zeros_like(cxd)  # all zeros = the regular grid layout with no overlap
+  v = torch.zeros_like(cxd)
+  a = torch.empty_like(cxd)
+  shape = _tile_shape(tuple(cxd.shape), ncomp)
+  # k0, k and stride are unused by the tile force; the stride only has to be well formed
+  pod = mesh._config_pod(dataclasses.replace(cfg, stride=(1, 1)), mesh._INPLANE)
+  dt, alpha, cap = np.float32(cfg.dt), np.float32(cfg.alpha), np.float32(cfg.start_cap)
+  t = 0
+  lib = _native.lib()
+  while t < cfg.max_iters:
+    c_dt, c_alpha, c_cap = (ctypes.c_float(float(dt)), ctypes.c_float(float(alpha)),
+                            ctypes.c_float(float(cap)))
+    n_pos, e_kin, v_max = ctypes.c_int32(0), ctypes.c_double(0), ctypes.c_float(0)
+    ctx.bind_stream()
+    rc = lib.sofima_tile_mesh_chunk(
+        ctx.handle, x.data_ptr(), v.data_ptr(), a.data_ptr(), cxd.data_ptr(), cyd.data_ptr(),
+        ctypes.byref(shape), ctypes.byref(pod), ctypes.byref(c_dt), ctypes.byref(c_alpha),
+        ctypes.byref(c_cap), ctypes.byref(n_pos), ctypes.byref(e_kin), ctypes.byref(v_max))
+    _native.check(ctx.handle, rc)
+    t += cfg.num_iters
+    if cfg.fire:
+      dt, alpha, cap = (np.float32(c_dt.value), np.float32(c_alpha.value),
+                        np.float32(c_cap.value))
+    if np.float32(v_max.value) < np.float32(cfg.stop_v_max):
+      if np.float32(cap) >= np.float32(cfg.final_cap):
+        break
+      cap = min(np.float32(cap) * np.float32(cfg.cap_scale), np.float32(cfg.final_cap))
+  return x.cpu().numpy()

@@ -251,13 +251,18 @@ def test_interpolate_missing_offsets_golden():
 
 
 def test_product_interpolate_missing_offsets_golden():
-  # host NumPy in the product too (as in the reference); the relaxation itself is not built
-  from sofima_b200 import stitch_rigid
+  # host NumPy in the product too (as in the reference); the relaxation itself runs on the
+  # device only (tests/test_tile_mesh_gpu.py) and fails loudly without one
+  import torch
+  from sofima_b200 import _native, stitch_rigid
   g = np.load(COARSE)
   for key, axis, kw in (('im_x', -1, {}), ('im_y', -2, {}), ('im_y_r2', -2, {'max_r': 2})):
     got = stitch_rigid.interpolate_missing_offsets(g['im_in'].copy(), axis, **kw)
     np.testing.assert_array_equal(got, g[key])
   with pytest.raises(ValueError):
     stitch_rigid.interpolate_missing_offsets(np.zeros((2, 3, 4)), -1)
-  with pytest.raises(NotImplementedError):
-    stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'])
+  with pytest.raises(NotImplementedError):  # only the built-in tile force fields
+    stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'], mesh_fn=lambda x, *a: x)
+  if not torch.cuda.is_available():
+    with pytest.raises(_native.NativeError):
+      stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'])

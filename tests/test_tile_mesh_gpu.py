@@ -1,0 +1,74 @@
+"""Rigid tile-grid step on the device: stitch_rigid.elastic_tile_mesh[_3d] and
+optimize_coarse_mesh (csrc/tile_mesh.cu, one thread block per chunk) against the golden
+vectors of the reference's own run (tests/golden/coarse_golden.npz).
+
+The arithmetic of the kernel is the header csrc/tile_mesh_core.cuh, which
+tests/test_tile_mesh_host.py compiles for the host and checks bit for bit without a GPU.
+The kernel itself was written after this round's GPU time had run out, so its first run on
+hardware is this test: it executes in a child process (a fault there cannot disturb the
+CUDA context of the other tests) and is marked xfail(strict=False) until it has been seen
+to pass on a B200."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'coarse_golden.npz')
+
+CHILD = r'''
+import ast, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from sofima_b200 import mesh, stitch_rigid
+g = np.load(sys.argv[2])
+out = {}
+out['force2'] = stitch_rigid.elastic_tile_mesh(g['cm2_x'], g['cm2_cx'], g['cm2_cy'])
+out['force3'] = stitch_rigid.elastic_tile_mesh_3d(g['cm3_x'], g['cm3_cx'], g['cm3_cy'])
+short = mesh.IntegrationConfig(**ast.literal_eval(str(g['cm2_short_cfg'])))
+out['short'] = stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'], short)
+out['opt2'] = stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'])
+out['opt3'] = stitch_rigid.optimize_coarse_mesh(g['cm3_cx'], g['cm3_cy'],
+                                                mesh_fn=stitch_rigid.elastic_tile_mesh_3d)
+damped = mesh.IntegrationConfig(dt=0.05, gamma=0.5, k0=0.0, k=0.1, stride=(1, 1),
+                                num_iters=50, max_iters=200, stop_v_max=0.0, fire=False)
+out['damped'] = stitch_rigid.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'], damped)
+# a grid larger than one block's thread count: 20 x 30 tiles
+rng = np.random.default_rng(5)
+cx = np.full((2, 1, 20, 30), np.nan, np.float32); cy = cx.copy()
+cx[0, 0, :, :-1] = -40 + rng.integers(-6, 7, (20, 29)); cx[1, 0, :, :-1] = rng.integers(-8, 9, (20, 29))
+cy[0, 0, :-1, :] = rng.integers(-8, 9, (19, 30)); cy[1, 0, :-1, :] = -30 + rng.integers(-6, 7, (19, 30))
+out['big_cx'], out['big_cy'] = cx, cy
+out['big'] = stitch_rigid.optimize_coarse_mesh(cx, cy, short)
+np.savez(sys.argv[3], **out)
+'''
+
+
+@pytest.mark.xfail(strict=False, reason='first run of csrc/tile_mesh.cu on hardware')
+def test_tile_mesh_matches_reference_run(tmp_path):
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  import ast
+  from oracle import stitch_oracle as so
+  from sofima_b200.mesh import IntegrationConfig
+  res = tmp_path / 'out.npz'
+  proc = subprocess.run([sys.executable, '-c', CHILD, ROOT, GOLDEN, str(res)],
+                        capture_output=True, text=True, timeout=300)
+  assert proc.returncode == 0, proc.stderr[-2000:]
+  out, g = np.load(res), np.load(GOLDEN)
+  np.testing.assert_array_equal(out['force2'], g['cm2_force'])
+  np.testing.assert_array_equal(out['force3'], g['cm3_force'])
+  np.testing.assert_array_equal(out['short'], g['cm2_short'])
+  np.testing.assert_array_equal(out['opt2'], g['cm2_opt'])
+  np.testing.assert_array_equal(out['opt3'], g['cm3_opt'])
+  short = IntegrationConfig(**ast.literal_eval(str(g['cm2_short_cfg'])))
+  damped = IntegrationConfig(dt=0.05, gamma=0.5, k0=0.0, k=0.1, stride=(1, 1), num_iters=50,
+                             max_iters=200, stop_v_max=0.0, fire=False)
+  np.testing.assert_array_equal(out['damped'],
+                                so.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'], damped))
+  np.testing.assert_array_equal(out['big'],
+                                so.optimize_coarse_mesh(out['big_cx'], out['big_cy'], short))
