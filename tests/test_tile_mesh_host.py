@@ -91,3 +91,64 @@ def test_relaxations(host):
   x, t = _relax(lib, native, g['cm2_cx'], g['cm2_cy'], damped)
   assert t == 200
   np.testing.assert_array_equal(x, so.optimize_coarse_mesh(g['cm2_cx'], g['cm2_cy'], damped))
+
+
+# ---- the kernel source itself, one emulated thread block on the host ---------------------
+EMU_SRC = os.path.join(ROOT, 'tests', 'host', 'tile_mesh_block_emu.cpp')
+EMU_FLAGS = ['-O1', '-g', '-ffp-contract=off', '-std=c++20', '-pthread']
+
+
+@pytest.fixture(scope='module')
+def emu(tmp_path_factory):
+  from sofima_b200 import _native
+  so = tmp_path_factory.mktemp('tile_emu') / 'libtile_mesh_emu.so'
+  subprocess.run(['g++'] + EMU_FLAGS + ['-shared', '-fPIC', '-o', str(so), EMU_SRC], check=True)
+  lib = ctypes.CDLL(str(so))
+  lib.tile_mesh_chunk_emu.argtypes = (
+      [F32P] * 5 + [ctypes.c_int] * 4 + [ctypes.POINTER(_native.IntegrationConfigPod)] +
+      [F32P, F32P, F32P, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double), F32P])
+  lib.tile_mesh_chunk_host = lib.tile_mesh_chunk_emu  # same signature: reuse _relax
+  return lib, _native
+
+
+def test_kernel_source_in_an_emulated_block(emu):
+  """tile_chunk_kernel compiled for the host (256 OS threads, __syncthreads = std::barrier,
+  __shared__ = static): the thread-block version of the chunk equals the reference's run."""
+  from sofima_b200 import mesh, stitch_rigid
+  from oracle import stitch_oracle as so
+  lib, native = emu
+  g = np.load(GOLDEN)
+  short = mesh.IntegrationConfig(**ast.literal_eval(str(g['cm2_short_cfg'])))
+  x, t = _relax(lib, native, g['cm2_cx'], g['cm2_cy'], short)
+  assert t == 300
+  np.testing.assert_array_equal(x, g['cm2_short'])
+  x, _ = _relax(lib, native, g['cm3_cx'], g['cm3_cy'], stitch_rigid.default_coarse_mesh_config())
+  np.testing.assert_array_equal(x, g['cm3_opt'])
+  # more tiles than threads, plain integrator
+  rng = np.random.default_rng(5)
+  cx = np.full((2, 1, 20, 30), np.nan, np.float32)
+  cy = cx.copy()
+  cx[0, 0, :, :-1] = -40 + rng.integers(-6, 7, (20, 29))
+  cx[1, 0, :, :-1] = rng.integers(-8, 9, (20, 29))
+  cy[0, 0, :-1, :] = rng.integers(-8, 9, (19, 30))
+  cy[1, 0, :-1, :] = -30 + rng.integers(-6, 7, (19, 30))
+  damped = mesh.IntegrationConfig(dt=0.05, gamma=0.5, k0=0.0, k=0.1, stride=(1, 1),
+                                  num_iters=50, max_iters=100, stop_v_max=0.0, fire=False)
+  x, _ = _relax(lib, native, cx, cy, damped)
+  np.testing.assert_array_equal(x, so.optimize_coarse_mesh(cx, cy, damped))
+  x, _ = _relax(lib, native, cx, cy, short)
+  np.testing.assert_array_equal(x, so.optimize_coarse_mesh(cx, cy, short))
+
+
+def test_kernel_source_is_race_free_under_tsan(tmp_path):
+  """The same emulation under ThreadSanitizer: a missing barrier or a node written by two
+  threads would be reported as a data race (checked by hand: dropping every third barrier
+  produces ten reports)."""
+  exe = tmp_path / 'tile_mesh_emu_tsan'
+  build = subprocess.run(['g++'] + EMU_FLAGS + ['-fsanitize=thread', '-DEMU_MAIN', '-o', str(exe),
+                                                EMU_SRC], capture_output=True, text=True)
+  if build.returncode != 0:
+    pytest.skip('ThreadSanitizer runtime not available: ' + build.stderr[-200:])
+  run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+  assert 'ThreadSanitizer' not in run.stderr, run.stderr[:2000]
+  assert run.returncode == 0 and run.stdout.count('fire=') == 4
