@@ -26,3 +26,28 @@ def test_peaks_fallback(tmp_path, monkeypatch):
       '{"hbm_gbs": 6500.0, "bf16_tflops_sustained": 1400.0}')
   p = bench._peaks()
   assert p['hbm_gbs'] == 6500.0 and p['tflops'] == 1400.0 and p['source'].startswith('measured')
+
+
+def test_committed_bench_lines_follow_the_contract():
+  """The last bench lines measured on a B200 (profiles/) carry every key the driver's
+  contract names -- a guard against dropping one while editing bench.py."""
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  line = json.load(open(os.path.join(root, 'profiles', 'bench_r1_l.json')))
+  for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+              'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'clocks',
+              'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+    assert key in line, key
+  assert line['metric'] == line['unit'] == 'patch-pairs/s' and line['vs_baseline'] is None
+  assert 'workload' in line['config'] and line['gpu_launches'] > 0
+  assert set(line['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
+  assert line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['value'] < line['value']
+  assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+  assert set(line['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'}
+  assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+  mesh = line['mesh']
+  assert mesh['roofline']['bound'] == 'hbm' and 0 < mesh['roofline']['frac'] < 1
+  assert mesh['cpu_baseline']['kind'] == 'port'
+  ref = json.load(open(os.path.join(root, 'profiles', 'bench_r1_l_reference_arm.json')))
+  assert ref['impl'] == 'reference' and ref['metric'] == line['metric']
+  assert ref['e2e']['h2d_bytes_per_step'] == 0 and ref['cpu_baseline']['value'] == ref['value']
