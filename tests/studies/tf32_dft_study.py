@@ -8,9 +8,10 @@ with the OPERANDS of every GEMM rounded to the tensor-core input format and fp32
 accumulation:
   tf32     one pass, operands rounded to 10 mantissa bits
   tf32x3   the 3-term split (hi*hi + hi*lo + lo*hi), i.e. fp32-grade products
-The correlation images then go through the oracle's peak search (oracle/flow_oracle.py).
+The correlation images then go through the oracle's peak search (oracle/flow_oracle.py);
+the study is test infrastructure (it lives under tests/ because it uses the oracle).
 
-  python tools/studies/tf32_dft_study.py            # prints one JSON line per workload
+  python tests/studies/tf32_dft_study.py            # prints one JSON line per workload
 """
 import json
 import os
