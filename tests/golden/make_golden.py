@@ -520,7 +520,35 @@ def coarse_cases(sr, mesh):
   return out
 
 
+def xcorr_numpy_branch_cases(ff):
+  """flow_field.masked_xcorr(use_jax=False) (flow_field.py:36-156): the reference's OWN NumPy
+  branch, i.e. real numpy.fft in float64 -- no stand-in for a JAX primitive is involved, so
+  these vectors pin the correlation / Padfield arithmetic independently of the shim."""
+  out = {}
+  rng = np.random.default_rng(51)
+  for tag, pshape, cshape in (('a', (2, 24, 30), (2, 24, 30)), ('b', (1, 17, 9), (1, 8, 13))):
+    prev = rng.standard_normal(pshape).astype(np.float32) * 20
+    curr = rng.standard_normal(cshape).astype(np.float32) * 20
+    pm = rng.random(pshape) > 0.8
+    cm = rng.random(cshape) > 0.75
+    out[f'xn_{tag}_prev'], out[f'xn_{tag}_curr'] = prev, curr
+    out[f'xn_{tag}_pm'], out[f'xn_{tag}_cm'] = pm, cm
+    out[f'xn_{tag}_plain'] = np.asarray(ff.masked_xcorr(prev, curr, use_jax=False))
+    out[f'xn_{tag}_masked'] = np.asarray(ff.masked_xcorr(prev, curr, pm, cm, use_jax=False))
+  prev = rng.standard_normal((9, 11, 12)).astype(np.float32)
+  curr = rng.standard_normal((4, 6, 5)).astype(np.float32)
+  out['xn_3d_prev'], out['xn_3d_curr'] = prev, curr
+  out['xn_3d_plain'] = np.asarray(ff.masked_xcorr(prev, curr, use_jax=False, dim=3))
+  return out
+
+
 def main():
+  if 'xcorr_numpy' in sys.argv[1:]:
+    ff = shim.load_reference('flow_field')
+    path = os.path.join(HERE, 'xcorr_numpy_golden.npz')
+    np.savez_compressed(path, **xcorr_numpy_branch_cases(ff))
+    print('xcorr_numpy_golden.npz', os.path.getsize(path) // 1024, 'KiB')
+    return
   if 'coarse' in sys.argv[1:]:
     sr = shim.load_reference('stitch_rigid')
     mesh = shim.load_reference('mesh')

@@ -149,3 +149,25 @@ def test_helpers():
   np.testing.assert_array_equal(s, want)
   assert [len(b) for b in fo.batch(list(range(10)), 4)] == [4, 4, 2]
   assert [fo.next_fast_len(n) for n in (319, 159, 255, 7, 1)] == [320, 160, 256, 8, 1]
+
+
+def test_reference_numpy_branch_golden():
+  """Oracle vs the reference's OWN NumPy branch, flow_field.masked_xcorr(use_jax=False)
+  (real numpy.fft -- no JAX stand-in involved; tests/golden/make_golden.py xcorr_numpy):
+  unmasked, Padfield-masked, unequal patch sizes, 3-d."""
+  import os
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'xcorr_numpy_golden.npz'))
+  for tag in ('a', 'b'):
+    prev, curr = g[f'xn_{tag}_prev'], g[f'xn_{tag}_curr']
+    want = g[f'xn_{tag}_plain']
+    got = fo.masked_xcorr(prev, curr)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * np.abs(want).max())
+    want = g[f'xn_{tag}_masked']
+    got = fo.masked_xcorr(prev, curr, g[f'xn_{tag}_pm'], g[f'xn_{tag}_cm'])
+    assert got.shape == want.shape and np.abs(want).max() > 0.1
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+  want = g['xn_3d_plain']
+  got = fo.masked_xcorr(g['xn_3d_prev'], g['xn_3d_curr'], dim=3)
+  assert got.shape == want.shape
+  np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * np.abs(want).max())
