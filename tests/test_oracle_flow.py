@@ -149,6 +149,8 @@ def test_helpers():
   np.testing.assert_array_equal(s, want)
   assert [len(b) for b in fo.batch(list(range(10)), 4)] == [4, 4, 2]
   assert [fo.next_fast_len(n) for n in (319, 159, 255, 7, 1)] == [320, 160, 256, 8, 1]
+  import scipy.fftpack  # the routine the reference calls (flow_field.py:67)
+  assert all(fo.next_fast_len(n) == scipy.fftpack.next_fast_len(n) for n in range(1, 17000))
 
 
 def test_reference_numpy_branch_golden():
