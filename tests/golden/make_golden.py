@@ -539,6 +539,11 @@ def xcorr_numpy_branch_cases(ff):
   curr = rng.standard_normal((4, 6, 5)).astype(np.float32)
   out['xn_3d_prev'], out['xn_3d_curr'] = prev, curr
   out['xn_3d_plain'] = np.asarray(ff.masked_xcorr(prev, curr, use_jax=False, dim=3))
+  prev = (rng.standard_normal((2, 9, 11, 12)) * 10).astype(np.float32)
+  curr = (rng.standard_normal((2, 9, 11, 12)) * 10).astype(np.float32)
+  pm, cm = rng.random(prev.shape) > 0.8, rng.random(curr.shape) > 0.75
+  out['xn_3dm_prev'], out['xn_3dm_curr'], out['xn_3dm_pm'], out['xn_3dm_cm'] = prev, curr, pm, cm
+  out['xn_3dm_masked'] = np.asarray(ff.masked_xcorr(prev, curr, pm, cm, use_jax=False, dim=3))
   return out
 
 

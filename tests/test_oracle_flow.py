@@ -173,3 +173,7 @@ def test_reference_numpy_branch_golden():
   got = fo.masked_xcorr(g['xn_3d_prev'], g['xn_3d_curr'], dim=3)
   assert got.shape == want.shape
   np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * np.abs(want).max())
+  want = g['xn_3dm_masked']  # batch of two masked 3-d volumes (batch-global thresholds)
+  got = fo.masked_xcorr(g['xn_3dm_prev'], g['xn_3dm_curr'], g['xn_3dm_pm'], g['xn_3dm_cm'], dim=3)
+  assert got.shape == want.shape and np.abs(want).max() > 0.1
+  np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
