@@ -1290,17 +1290,29 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
 }  // namespace sofima
 
 #include "flow3d.cuh"
+#include "flow3d_masked.cuh"
 
 namespace sofima {
 namespace flow {
+
+static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                             const void* post_img, const uint8_t* pre_mask,
+                             const uint8_t* post_mask, const int32_t* pre_starts,
+                             const int32_t* post_starts, long long B, float* images);
 
 // 3-d correlation images of one batch into `images` [B][sz][sy][sx] (unmasked).
 static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
                       const void* post_img, const uint8_t* pre_mask, const uint8_t* post_mask,
                       const int32_t* pre_starts, const int32_t* post_starts, long long B,
                       float* images) {
-  if (pre_mask || post_mask)
-    return fail(ctx, SOFIMA_EUNSUPPORTED, "masked 3-d correlation is not built yet");
+  if (pre_mask || post_mask) {
+    // flow3d_masked.cuh has not run on hardware yet: opt-in until its test has passed.
+    const char* e = getenv("SOFIMA_EXPERIMENTAL_MASKED3D");
+    if (!e || e[0] != '1')
+      return fail(ctx, SOFIMA_EUNSUPPORTED, "masked 3-d correlation is not built yet");
+    return run_xcorr3_masked(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
+                             post_starts, B, images);
+  }
   Problem3 P;
   memset(&P, 0, sizeof(P));
   P.dtype = p->img_dtype;
@@ -1416,6 +1428,157 @@ static void peak_params(const sofima_xcorr_params* p, PeakParams* pp) {
   pp->cz = c[0]; pp->cy = c[1]; pp->cx = c[2];
   pp->md = p->min_distance;
   pp->thr_rel = p->threshold_rel;
+}
+
+// Masked 3-d correlation images of one batch (flow_field.py:91-155, dim = 3); see
+// flow3d_masked.cuh.  Same contract as run_xcorr3.
+static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                             const void* post_img, const uint8_t* pre_mask,
+                             const uint8_t* post_mask, const int32_t* pre_starts,
+                             const int32_t* post_starts, long long B, float* images) {
+  Problem3M P;
+  memset(&P, 0, sizeof(P));
+  P.dtype = p->img_dtype;
+  const void* datas[2] = {pre_img, post_img};
+  const uint8_t* masks[2] = {pre_mask, post_mask};
+  const int64_t* shapes[2] = {p->pre_shape, p->post_shape};
+  const int64_t* mshapes[2] = {p->pre_mask_shape, p->post_mask_shape};
+  const int32_t* patches[2] = {p->pre_patch, p->post_patch};
+  for (int i = 0; i < 2; ++i) {
+    Vol3M& I = P.img[i];
+    I.data = datas[i];
+    I.mask = masks[i];
+    I.d = (int)shapes[i][0]; I.h = (int)shapes[i][1]; I.w = (int)shapes[i][2];
+    I.pd = patches[i][0]; I.ph = patches[i][1]; I.pw = patches[i][2];
+    I.md = masks[i] ? (int)mshapes[i][0] : I.d;
+    I.mh = masks[i] ? (int)mshapes[i][1] : I.h;
+    I.mw = masks[i] ? (int)mshapes[i][2] : I.w;
+    if (masks[i] && (I.md < I.pd || I.mh < I.ph || I.mw < I.pw))
+      return fail(ctx, SOFIMA_EINVAL, "mask smaller than the patch");
+  }
+  P.starts[0] = pre_starts;
+  P.starts[1] = post_starts;
+  P.has_mean = p->has_mean;
+  P.mean = p->mean;
+  P.sz = p->pre_patch[0] + p->post_patch[0] - 1;
+  P.sy = p->pre_patch[1] + p->post_patch[1] - 1;
+  P.sx = p->pre_patch[2] + p->post_patch[2] - 1;
+  P.Lz = next_fast_len(P.sz); P.Ly = next_fast_len(P.sy); P.Lx = next_fast_len(P.sx);
+  FftPlan Fz, Fy, Fx;
+  int rc;
+  if ((rc = make_plan(ctx, P.Lz, &Fz))) return rc;
+  if ((rc = make_plan(ctx, P.Ly, &Fy))) return rc;
+  if ((rc = make_plan(ctx, P.Lx, &Fx))) return rc;
+  const long long vol = (long long)P.Lz * P.Ly * P.Lx;
+  const size_t img_elems = (size_t)P.sz * P.sy * P.sx;
+  // per pair: 6 forward + 6 product volumes
+  long long nsub = (long long)((1024ull << 20) / (12 * vol * sizeof(float2)));
+  if (nsub < 1) nsub = 1;
+  if (nsub > B) nsub = B;
+  void *Z = nullptr, *W = nullptr, *means = nullptr, *ov = nullptr, *den = nullptr,
+       *loc = nullptr, *maxima = nullptr;
+  if ((rc = scratch(ctx, "flow3m.Z", sizeof(float2) * 6 * nsub * vol, &Z))) return rc;
+  if ((rc = scratch(ctx, "flow3m.W", sizeof(float2) * 6 * nsub * vol, &W))) return rc;
+  if ((rc = scratch(ctx, "flow3m.means", sizeof(float) * 2 * B, &means))) return rc;
+  if ((rc = scratch(ctx, "flow3m.ov", sizeof(float) * B * img_elems, &ov))) return rc;
+  if ((rc = scratch(ctx, "flow3m.den", sizeof(float) * B * img_elems, &den))) return rc;
+  if ((rc = scratch(ctx, "flow3m.loc", sizeof(float) * 3 * nsub * img_elems, &loc))) return rc;
+  if ((rc = scratch(ctx, "flow3m.maxima", sizeof(float) * 2, &maxima))) return rc;
+  SOFIMA_CUDA(ctx, cudaMemsetAsync(maxima, 0, sizeof(float) * 2, ctx->stream));
+  const size_t smem_cap = 200 * 1024;
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(axis_fft_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(axis_fft_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_cap));
+  auto lines_per_block = [&](int L) {
+    int C = 16;
+    while (C > 1 && (size_t)(2 * C + 1) * L * sizeof(float2) > 96 * 1024) C /= 2;
+    return C;
+  };
+  // in-place transforms over x, y, z (forward) / z, y, x (inverse) of nvol volumes
+  auto transform = [&](float2* data, bool inverse, long long nvol) -> int {
+    struct Axis { const FftPlan* F; long long nlines, inner, istride, ostride, es; };
+    const long long plane = (long long)P.Ly * P.Lx;
+    const Axis axes[3] = {
+        {&Fx, nvol * P.Lz * P.Ly, 1, 0, P.Lx, 1},
+        {&Fy, nvol * P.Lz * P.Lx, P.Lx, 1, plane, P.Lx},
+        {&Fz, nvol * plane, plane, 1, vol, plane},
+    };
+    for (int a = 0; a < 3; ++a) {
+      const Axis& A = axes[inverse ? 2 - a : a];
+      const int C = lines_per_block(A.F->L);
+      const size_t smem = (size_t)(2 * C + 1) * A.F->L * sizeof(float2);
+      const unsigned grid = (unsigned)ceil_div<long long>(A.nlines, C);
+      LaunchTimer timer(ctx, "flow3_fft");
+      if (inverse)
+        axis_fft_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(
+            data, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+      else
+        axis_fft_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(
+            data, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    return SOFIMA_OK;
+  };
+  const float scale = (float)(1.0 / ((double)P.Lx * P.Ly * P.Lz));
+  float* ov_all = static_cast<float*>(ov);
+  float* den_all = static_cast<float*>(den);
+  float* locf = static_cast<float*>(loc);
+  for (long long b0 = 0; b0 < B; b0 += nsub) {
+    const int nb = (int)((B - b0 < nsub) ? (B - b0) : nsub);
+    P.b0 = b0;
+    P.nb = nb;
+    float2* Zp = static_cast<float2*>(Z);
+    float2* Wp = static_cast<float2*>(W);
+    {
+      LaunchTimer timer(ctx, "flow3_pack");
+      patch_mean3m_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, (float*)means);
+      SOFIMA_CHECK_LAUNCH(ctx);
+      pack3m_kernel<<<dim3(ctx->num_sms * 2, 6, nb), kThreads, 0, ctx->stream>>>(
+          P, (const float*)means, Zp);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    if ((rc = transform(Zp, false, 6ll * nb))) return rc;
+    {
+      LaunchTimer timer(ctx, "flow3_mul");
+      multiply3m_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(Zp, Wp,
+                                                                        (long long)nb * vol);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    if ((rc = transform(Wp, true, 6ll * nb))) return rc;
+    Outputs3M outs;
+    // whole-batch arrays are addressed with the global pair index, sub-batch-local ones
+    // with the index inside the sub-batch
+    outs.dst[0] = images;          outs.first[0] = b0;   // numerator -> result
+    outs.dst[1] = ov_all;          outs.first[1] = b0;   // overlap
+    outs.dst[2] = den_all;         outs.first[2] = b0;   // mc_p -> denominator
+    outs.dst[3] = locf;                              outs.first[3] = 0;  // mc_c
+    outs.dst[4] = locf + (size_t)nsub * img_elems;   outs.first[4] = 0;  // p_sq
+    outs.dst[5] = locf + 2 * (size_t)nsub * img_elems; outs.first[5] = 0;  // c_sq
+    {
+      LaunchTimer timer(ctx, "flow3_crop");
+      crop3m_kernel<<<dim3(ctx->num_sms, 6, nb), kThreads, 0, ctx->stream>>>(P, Wp, outs, scale);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+    {
+      const long long n = (long long)nb * img_elems;
+      const size_t off = (size_t)b0 * img_elems;
+      LaunchTimer timer(ctx, "flow_padfield_terms");
+      padfield_terms_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+          images + off, ov_all + off, den_all + off, locf, locf + (size_t)nsub * img_elems,
+          locf + 2 * (size_t)nsub * img_elems, n, (float*)maxima);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+  }
+  {
+    LaunchTimer timer(ctx, "flow_padfield_norm");
+    padfield_normalise_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+        images, ov_all, den_all, (long long)B * img_elems, (const float*)maxima);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  return SOFIMA_OK;
 }
 
 }  // namespace flow

@@ -174,7 +174,9 @@ def masked_xcorr(prev, curr, prev_mask=None, curr_mask=None, use_jax: bool = Fal
   curr = np.asarray(curr, dtype=np.float32)
   if dim not in (2, 3):
     raise NotImplementedError(f'correlation over {dim} axes: only 2 and 3 are built')
-  if dim == 3 and (prev_mask is not None or curr_mask is not None):
+  if (dim == 3 and (prev_mask is not None or curr_mask is not None)
+      and os.environ.get('SOFIMA_EXPERIMENTAL_MASKED3D') != '1'):
+    # csrc/flow3d_masked.cuh exists but has not run on hardware yet
     raise NotImplementedError('masked 3-d correlation is not part of the CUDA backend yet')
   lead = prev.shape[:-dim]
   pb = prev.reshape((-1,) + prev.shape[-dim:])
