@@ -65,14 +65,3 @@ def test_masked_3d_correlation(tmp_path):
   got = out['flow']
   np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
   np.testing.assert_array_equal(got[:3], want[:3])
-
-
-def test_masked_3d_is_opt_in():
-  import torch
-  if not torch.cuda.is_available():
-    pytest.skip('needs a CUDA device')
-  from sofima_b200 import flow_field as ff
-  assert os.environ.get('SOFIMA_EXPERIMENTAL_MASKED3D') != '1'
-  a = np.zeros((6, 6, 6), np.float32)
-  with pytest.raises(NotImplementedError):
-    ff.masked_xcorr(a, a, np.zeros(a.shape, bool), None, dim=3)
