@@ -280,19 +280,37 @@ def cpu_flow_sample(size, seed=0):
   return pre, post
 
 
-def time_cpu_flow(size, reps=1):
-  """Oracle flow_field (NumPy/pocketfft, all cores) on one size x size tile pair."""
-  from oracle import flow_oracle
-  pre, post = cpu_flow_sample(size)
-  calc = flow_oracle.MaskedXCorrWithStatsCalculator()
-  g = (size - (PATCH - STEP)) // STEP
-  best = float('inf')
-  for _ in range(reps):
+class CpuFlowArm:
+  """The reference's unit of work on the CPU: one `batched_xcorr_peaks` call
+  (flow_field.py:385-441, the jit boundary) on a whole reference batch of BATCH = 1024
+  patch pairs of the SAME 4096 x 4096 tile pair, patch 160, step 40, that the GPU arm
+  runs -- oracle/flow_oracle.py (NumPy + pocketfft fp32, all host threads)."""
+
+  def __init__(self, size=FLOW_TILE):
+    from oracle import flow_oracle
+    self.fo = flow_oracle
+    self.pre, self.post = cpu_flow_sample(size)
+    g = (size - (PATCH - STEP)) // STEP
+    oyx = np.array(np.where(np.ones((g, g), bool))).T
+    self.batches = []
+    for i in range(0, len(oyx), BATCH):       # flow_field.py:610-623
+      pos = oyx[i:i + BATCH]
+      real = pos.shape[0]
+      if real < BATCH:
+        pos = np.pad(pos, ((0, BATCH - real), (0, 0)), mode='edge')
+      self.batches.append((pos * STEP, real))
+
+  def step(self, i):
+    """One reference batch; returns (patch pairs computed, seconds)."""
+    starts, real = self.batches[i % len(self.batches)]
     t0 = time.perf_counter()
-    out = calc.flow_field(pre, post, PATCH, STEP, batch_size=256)
-    best = min(best, time.perf_counter() - t0)
-  assert out.shape == (4, g, g)
-  return g * g / best, g * g, best
+    peaks = self.fo.batched_xcorr_peaks(self.pre, self.post, None, None, (PATCH, PATCH),
+                                        starts, None, post_starts=starts)
+    sec = time.perf_counter() - t0
+    assert peaks.shape == (BATCH, 4)
+    ok = peaks[:real]
+    assert np.all(ok[:, 0] == -4) and np.all(ok[:, 1] == 3), 'cpu arm parity'
+    return BATCH, sec
 
 
 def time_cpu_mesh(n, iters, reps=1):
@@ -322,13 +340,12 @@ def run_reference(args):
   if rank != 0:
     return
   cores = len(os.sched_getaffinity(0))
-  os.environ.setdefault('OMP_NUM_THREADS', str(cores))
-  size = 1024  # bounded sample: (1024-120)//40 = 22 -> 484 patch pairs per step
-  for _ in range(args.warmup):
-    time_cpu_flow(size)
+  arm = CpuFlowArm()
+  for i in range(args.warmup):
+    arm.step(i)
   pairs, flow_s = 0, 0.0
-  for _ in range(args.steps):
-    _, n, sec = time_cpu_flow(size)  # times flow_field only, not the synthesis
+  for i in range(args.steps):
+    n, sec = arm.step(args.warmup + i)
     pairs += n
     flow_s += sec
   flow_v = pairs / flow_s
@@ -346,13 +363,16 @@ def run_reference(args):
       'warmup': args.warmup, 'ms_per_step': flow_s / args.steps * 1e3,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': f'flow_field on a {size}x{size} crop of the 4096x4096 '
-                             f'uint8 tile pair, patch {PATCH}, step {STEP} '
-                             '(bounded CPU sample of the same workload)'},
+      'config': {'workload': f'flow_field on one {FLOW_TILE}x{FLOW_TILE} uint8 tile pair, patch '
+                             f'{PATCH}, step {STEP}, batch {BATCH}; a CPU step is ONE reference '
+                             f'batch of {BATCH} patch pairs of that tile pair (bounded sample '
+                             'of the same workload, same tile size and batch size)'},
       'cpu_baseline': {'value': flow_v, 'unit': 'patch-pairs/s', 'cores': cores,
                        'kind': 'port',
-                       'sample': f'{args.steps} x {size}^2 tile pair (484 patch pairs), '
-                                 'oracle/flow_oracle.py, pocketfft fp32'},
+                       'sample': f'{args.steps} reference batches of {BATCH} patch pairs of the '
+                                 f'{FLOW_TILE}^2 tile pair, oracle/flow_oracle.py '
+                                 '(batched_xcorr_peaks), pocketfft fp32, '
+                                 f'OMP_NUM_THREADS={os.environ.get("OMP_NUM_THREADS")}'},
       'e2e': {'value': flow_v, 'unit': 'patch-pairs/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
       'mesh': {'metric': 'node-updates/s', 'value': mesh_v, 'unit': 'node-updates/s',
@@ -743,11 +763,17 @@ def run_ours(args):
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     cores = len(os.sched_getaffinity(0))
     if 'metric' in result:
-      v, n, s = time_cpu_flow(1536)
+      arm = CpuFlowArm()
+      arm.step(0)
+      n_cpu, s_cpu = 0, 0.0
+      for i in range(6):
+        n, sec = arm.step(1 + i)
+        n_cpu += n
+        s_cpu += sec
       result['cpu_baseline'] = {
-          'value': v, 'unit': 'patch-pairs/s', 'cores': cores, 'kind': 'port',
-          'sample': f'one 1536^2 crop ({n} patch pairs, {s:.1f} s), '
-                    'oracle/flow_oracle.py on pocketfft fp32'}
+          'value': n_cpu / s_cpu, 'unit': 'patch-pairs/s', 'cores': cores, 'kind': 'port',
+          'sample': f'6 reference batches of {BATCH} patch pairs of the same {FLOW_TILE}^2 tile '
+                    f'pair ({s_cpu:.1f} s), oracle/flow_oracle.py on pocketfft fp32'}
     if 'mesh' in result:
       v, s, threads = time_cpu_mesh(MESH_N, 40)
       result['mesh']['cpu_baseline'] = {
@@ -811,6 +837,15 @@ def main():
   if args.warmup < 3 and args.impl == 'ours':
     args.warmup = max(args.warmup, 1)
   if args.impl == 'reference':
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to
+    # use every host core, and OpenMP / OpenBLAS read the variable when they are loaded --
+    # so it is set and the interpreter re-executed before anything else happens.
+    cores = str(len(os.sched_getaffinity(0)))
+    if int(os.environ.get('RANK', '0')) == 0 and os.environ.get('OMP_NUM_THREADS') != cores:
+      env = dict(os.environ, OMP_NUM_THREADS=cores, SOFIMA_BENCH_REEXEC='1')
+      if not os.environ.get('SOFIMA_BENCH_REEXEC'):
+        os.dup2(_REAL_STDOUT.fileno(), 1)
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
     run_reference(args)
   else:
     run_ours(args)

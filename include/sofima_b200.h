@@ -43,6 +43,11 @@ int sofima_abi_version(void);
  * written to a host buffer, and clears the records. */
 int sofima_ctx_set_timing(sofima_ctx* ctx, int on);
 int sofima_ctx_timing_report(sofima_ctx* ctx, char* buf, int64_t buf_len);
+/* Frees every cached scratch buffer larger than `keep_bytes` (the flow path keeps its
+ * row-spectra cache and spectra scratch, several GB after a large call, for the next call
+ * of the same geometry).  Synchronises the stream.  No reference counterpart: JAX frees
+ * its temporaries when the jitted call returns (flow_field.py:683). */
+int sofima_ctx_trim(sofima_ctx* ctx, int64_t keep_bytes);
 /* Number of kernel launches issued through `ctx` so far (bench "gpu_launches"). */
 int64_t sofima_ctx_launch_count(const sofima_ctx* ctx);
 

@@ -9,3 +9,12 @@ fallback: without the built library and a B200 the calls raise.
 """
 
 __version__ = '0.1.0'
+
+
+def release_memory(keep_bytes: int = 0, device=None) -> None:
+  """Frees the calling thread's cached device scratch (row-spectra cache, spectra and image
+  scratch of the flow path; several GB after a large `flow_field` call) so that other
+  users of the GPU -- torch's allocator, the mesh solver -- can have it.  Optional: the
+  buffers are otherwise kept for the next call of the same geometry."""
+  from . import _native
+  _native.Context.get(device).trim(keep_bytes)

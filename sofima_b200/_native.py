@@ -154,6 +154,7 @@ _PROTOS = {
     'sofima_ctx_launch_count': (ctypes.c_int64, [_vp]),
     'sofima_ctx_set_timing': (ctypes.c_int, [_vp, ctypes.c_int]),
     'sofima_ctx_timing_report': (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
+    'sofima_ctx_trim': (ctypes.c_int, [_vp, ctypes.c_int64]),
     'sofima_mesh_force': (ctypes.c_int, [
         _vp, ctypes.c_int, _vp, ctypes.POINTER(MeshShape), ctypes.c_double,
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, _vp]),
@@ -263,9 +264,15 @@ def check(ctx_handle, rc: int):
 
 
 class Context:
-  """A sofima_ctx bound to one CUDA device and the torch stream current at use."""
+  """A sofima_ctx bound to one CUDA device and the torch stream current at use.
 
-  _per_device: dict[int, 'Context'] = {}
+  include/sofima_b200.h: "one context per host thread" -- a sofima_ctx owns its stream
+  binding and its scratch buffers and is not re-entrant (ctypes releases the GIL during
+  the native calls).  `get()` therefore hands every Python thread its own context per
+  device; threads that share a GPU hold separate scratch memory.
+  """
+
+  _per_device: dict[tuple[int, int], 'Context'] = {}
   _lock = threading.Lock()
 
   def __init__(self, device: int):
@@ -289,11 +296,18 @@ class Context:
         raise NativeError(
             'No CUDA device: sofima_b200 runs on B200 only (no CPU fallback).')
       device = torch.cuda.current_device()
+    key = (int(device), threading.get_ident())
     with cls._lock:
-      ctx = cls._per_device.get(device)
+      ctx = cls._per_device.get(key)
       if ctx is None:
-        ctx = cls._per_device[device] = Context(device)
+        ctx = cls._per_device[key] = Context(device)
     return ctx
+
+  def trim(self, keep_bytes: int = 0):
+    """Frees the context's grow-only scratch buffers larger than `keep_bytes` (the flow
+    path's row-spectra cache and spectra scratch can hold several GB after one large
+    call).  Synchronises the stream."""
+    check(self.handle, lib().sofima_ctx_trim(self.handle, int(keep_bytes)))
 
   def bind_stream(self):
     stream = self._torch.cuda.current_stream(self.device).cuda_stream

@@ -103,6 +103,23 @@ int sofima_ctx_timing_report(sofima_ctx* ctx, char* buf, int64_t buf_len) {
   return SOFIMA_OK;
 }
 
+int sofima_ctx_trim(sofima_ctx* ctx, int64_t keep_bytes) {
+  if (!ctx) return sofima::fail(nullptr, SOFIMA_EINVAL, "ctx is NULL");
+  sofima::DeviceGuard guard(ctx->device);
+  SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->rowcache.valid = false;  // its spectra live in scratch buffers
+  ctx->rowfix_key[0] = 0;
+  for (auto it = ctx->scratch.begin(); it != ctx->scratch.end();) {
+    if (it->second.ptr && (int64_t)it->second.bytes > keep_bytes) {
+      SOFIMA_CUDA(ctx, cudaFree(it->second.ptr));
+      it = ctx->scratch.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  return SOFIMA_OK;
+}
+
 int64_t sofima_ctx_launch_count(const sofima_ctx* ctx) {
   return ctx ? ctx->launches : 0;
 }

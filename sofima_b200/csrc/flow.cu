@@ -1306,10 +1306,6 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
                       const int32_t* pre_starts, const int32_t* post_starts, long long B,
                       float* images) {
   if (pre_mask || post_mask) {
-    // flow3d_masked.cuh has not run on hardware yet: opt-in until its test has passed.
-    const char* e = getenv("SOFIMA_EXPERIMENTAL_MASKED3D");
-    if (!e || e[0] != '1')
-      return fail(ctx, SOFIMA_EUNSUPPORTED, "masked 3-d correlation is not built yet");
     return run_xcorr3_masked(ctx, p, pre_img, post_img, pre_mask, post_mask, pre_starts,
                              post_starts, B, images);
   }

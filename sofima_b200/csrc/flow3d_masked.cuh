@@ -5,9 +5,8 @@
 // batch-global maxima are the dimension-agnostic kernels of the 2-d path
 // (padfield_terms_kernel / padfield_normalise_kernel).
 //
-// STATUS: written after the GPU time of round 1 had run out -- not yet run on hardware.
-// The entry point stays behind SOFIMA_EXPERIMENTAL_MASKED3D=1 (run_xcorr3 returns
-// SOFIMA_EUNSUPPORTED otherwise) until tests/test_masked3d_gpu.py has passed on a B200.
+// Checked on a B200 against golden vectors of the reference's NumPy branch
+// (tests/test_masked3d_gpu.py).
 #pragma once
 
 namespace sofima {

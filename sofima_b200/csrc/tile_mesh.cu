@@ -62,6 +62,13 @@ int sofima_tile_mesh_chunk(sofima_ctx* ctx, float* x, float* v, float* a, const 
   if (cfg->remove_drift)
     return fail(ctx, SOFIMA_EUNSUPPORTED, "tile mesh: remove_drift is not built");
   if (cfg->num_iters < 0) return fail(ctx, SOFIMA_EINVAL, "num_iters < 0");
+  // One thread block walks all nodes in every step: a tile grid is tens to a few thousand
+  // nodes (one per image tile).  Anything far beyond that would keep a single SM busy for
+  // minutes without a way to interrupt it, so it is refused instead.
+  constexpr long long kMaxTileNodes = 1 << 16;
+  if (s.nodes() > kMaxTileNodes)
+    return fail(ctx, SOFIMA_EUNSUPPORTED, "tile mesh: %lld nodes exceed the single-block "
+                "solver's limit of %lld", (long long)s.nodes(), kMaxTileNodes);
   DeviceGuard guard(ctx->device);
 
   const tilemesh::Chunk k = tilemesh::make_chunk(*cfg);

@@ -174,10 +174,6 @@ def masked_xcorr(prev, curr, prev_mask=None, curr_mask=None, use_jax: bool = Fal
   curr = np.asarray(curr, dtype=np.float32)
   if dim not in (2, 3):
     raise NotImplementedError(f'correlation over {dim} axes: only 2 and 3 are built')
-  if (dim == 3 and (prev_mask is not None or curr_mask is not None)
-      and os.environ.get('SOFIMA_EXPERIMENTAL_MASKED3D') != '1'):
-    # csrc/flow3d_masked.cuh exists but has not run on hardware yet
-    raise NotImplementedError('masked 3-d correlation is not part of the CUDA backend yet')
   lead = prev.shape[:-dim]
   pb = prev.reshape((-1,) + prev.shape[-dim:])
   cb = curr.reshape((-1,) + curr.shape[-dim:])
@@ -442,7 +438,7 @@ class _FlowJob:
       rows_direct = starts_h.shape[1] * starts_h.shape[2] * (patch_size[0] + post_patch_size[0])
       rows_shared = len(xs[0]) * int(pre_shape[0]) + len(xs[1]) * int(post_shape[0])
       spec_bytes = rows_shared * (sum(patch_size[1:]) + sum(post_patch_size[1:])) * 4 + 1
-      self._share_rows = (rows_shared < 0.6 * rows_direct and spec_bytes < (8 << 30))
+      self._share_rows = (rows_shared < 0.6 * rows_direct and spec_bytes < (4 << 30))
 
   def run(self, pre_d, post_d, pre_m=None, post_m=None, mean=None, min_distance=2,
           peak_radius=5, progress_fn=_silent_fn, out=None):
@@ -507,7 +503,7 @@ def _cached_job(ctx, oyx, pre_shape, post_shape, patch_size, post_patch_size, st
   if pre_tf is not None or post_tf is not None:
     return _FlowJob(ctx, oyx, pre_shape, post_shape, patch_size, post_patch_size, step,
                     batch_size, pre_tf, pre_ts, post_tf, post_ts)
-  key = (ctx.device, tuple(pre_shape), tuple(post_shape), tuple(patch_size),
+  key = (ctx.device, threading.get_ident(), tuple(pre_shape), tuple(post_shape), tuple(patch_size),
          tuple(post_patch_size), tuple(step), int(batch_size), oyx.shape,
          hash(np.ascontiguousarray(oyx).tobytes()))
   with _JOB_CACHE_LOCK:

@@ -27,6 +27,16 @@ def _as_vec(value, dim: int):
   return tuple(value)
 
 
+def _integral_starts(start, dim: int, name: str) -> list[int]:
+  """The C ABI carries map origins as int64 (every caller in the reference passes box
+  corners); a fractional origin would silently shift the composed map, so it is refused."""
+  vals = np.asarray(start, dtype=np.float64).reshape(-1)[-dim:]
+  if not np.all(np.isfinite(vals)) or np.any(vals != np.round(vals)):
+    raise ValueError(f'{name} must be integral (got {vals.tolist()}): fractional map '
+                     'origins are not supported by the CUDA backend')
+  return [int(v) for v in vals]
+
+
 def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,
                       start2: Sequence[float], stride2, mode='nearest'):
   """Composes two coordinate maps: map2(map1(z, y, x)) on the grid of map1.
@@ -52,8 +62,8 @@ def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,
     raise NotImplementedError(f"mode {mode!r}: only 'nearest' and 'constant' are built")
   stride1 = _as_vec(stride1, dim)
   stride2 = _as_vec(stride2, dim)
-  s1 = [int(v) for v in np.asarray(start1).reshape(-1)[-dim:]]
-  s2 = [int(v) for v in np.asarray(start2).reshape(-1)[-dim:]]
+  s1 = _integral_starts(start1, dim, 'start1')
+  s2 = _integral_starts(start2, dim, 'start2')
   if len(s1) != dim or len(s2) != dim:
     raise ValueError('start1 / start2 need at least `dim` entries')
   if dim == 2 and map1.shape[1] != map2.shape[1]:

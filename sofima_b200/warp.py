@@ -75,10 +75,13 @@ def ndimage_warp(image, coord_map: np.ndarray, stride: Sequence[float],
   labels_back = None
   if not _mesh._is_tensor(image) and image.dtype == np.uint64:
     # Label volumes: contiguous ids, nearest neighbour (warp.py:240-243).
-    ids, inverse = np.unique(image, return_inverse=True)
+    # Id 0 (background) is pinned at index 0 whether or not it occurs in the volume, as
+    # labels.make_contiguous does upstream: the kernel writes cval = 0 for samples outside
+    # the image, and that has to read back as label 0, not as the smallest real label.
+    ids = np.unique(np.append(image.ravel(), np.uint64(0)))
     if len(ids) >= 2**32:
       raise ValueError('too many distinct labels')
-    image = inverse.reshape(image.shape).astype(np.uint32)
+    image = np.searchsorted(ids, image).astype(np.uint32)
     labels_back, order = ids, 0
 
   src_map = _to_absolute(np.asarray(coord_map), stride)

@@ -122,9 +122,14 @@ def test_3d_textures_match_oracle(ff):
                                 np.array([[0, 0, 0], [7, 19, 20], [14, 38, 40]]), None)
   np.testing.assert_allclose(ff._batched_peaks(xc, center, 2, 0.5, (2, 3, 4)),
                              fo.batched_peaks(xc, center, 2, 0.5, (2, 3, 4)), rtol=1e-5)
-  with pytest.raises(NotImplementedError):  # masked 3-d: fails loudly
-    ff.JAXMaskedXCorrWithStatsCalculator().flow_field(
-        pre, post, pre_mask=np.zeros(pre.shape, bool), **kw)
+  # masked 3-d patches (csrc/flow3d_masked.cuh): an all-valid mask goes through the
+  # Padfield path and must still agree with the oracle's masked path
+  m0 = np.zeros(pre.shape, bool)
+  got_m = ff.JAXMaskedXCorrWithStatsCalculator(peak_radius=(2, 3, 4)).flow_field(
+      pre, post, pre_mask=m0, **kw)
+  want_m = fo.MaskedXCorrWithStatsCalculator(peak_radius=(2, 3, 4)).flow_field(
+      pre, post, pre_mask=m0, **kw)
+  _check_flow(got_m, want_m)
 
 
 # ---- golden vectors from the reference source -------------------------------------
@@ -364,5 +369,8 @@ def test_masked_xcorr_3d_unequal_volumes(ff):
   b2 = ff.masked_xcorr(np.stack([search, search]), np.stack([query, -query]), dim=3)
   np.testing.assert_allclose(b2[0] / scale, want / scale, atol=3e-6)
   np.testing.assert_allclose(b2[1] / scale, -want / scale, atol=3e-6)
-  with pytest.raises(NotImplementedError):
-    ff.masked_xcorr(search, query, np.zeros(search.shape, bool), None, dim=3)
+  sm = np.zeros(search.shape, bool)
+  sm[:5, :7, :9] = True
+  got_m = ff.masked_xcorr(search, query, sm, None, dim=3)
+  want_m = fo.masked_xcorr(search, query, sm, None, dim=3)
+  np.testing.assert_allclose(got_m, want_m, rtol=0, atol=2e-4)

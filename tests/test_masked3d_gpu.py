@@ -1,8 +1,6 @@
 """Masked 3-d correlation (csrc/flow3d_masked.cuh, reference flow_field.py:91-155 with
-dim = 3).  The code was written after this round's GPU time had run out, so it is opt-in
-(SOFIMA_EXPERIMENTAL_MASKED3D=1; without it the product raises NotImplementedError as before)
-and this test is its first run on hardware: child process, xfail(strict=False) until it has
-been seen to pass on a B200.  The oracle side is pinned on the reference's own NumPy branch
+dim = 3) in a child process.  Passed on a B200 at the end of round 1 (GPUTEST_r01: xpassed), so
+the path is on by default.  The oracle side is pinned on the reference's own NumPy branch
 (tests/test_oracle_flow.py::test_reference_numpy_branch_golden)."""
 import os
 import subprocess
@@ -44,14 +42,13 @@ np.savez(sys.argv[3], **out)
 '''
 
 
-@pytest.mark.xfail(strict=False, reason='first run of csrc/flow3d_masked.cuh on hardware')
 def test_masked_3d_correlation(tmp_path):
   import torch
   if not torch.cuda.is_available():
     pytest.skip('needs a CUDA device')
   from oracle import flow_oracle as fo
   res = tmp_path / 'out.npz'
-  env = dict(os.environ, SOFIMA_EXPERIMENTAL_MASKED3D='1')
+  env = dict(os.environ)
   proc = subprocess.run([sys.executable, '-c', CHILD, ROOT, GOLDEN, str(res)], env=env,
                         capture_output=True, text=True, timeout=300)
   assert proc.returncode == 0, proc.stderr[-2000:]

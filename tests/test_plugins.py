@@ -206,13 +206,9 @@ def test_decorator_chunk_functions():  # decorators/flow_test.py:55-88
     dflow.OptimFlow()
 
 
-def test_masked_3d_correlation_is_opt_in(monkeypatch):
-  # csrc/flow3d_masked.cuh is dormant until it has run on hardware: without the opt-in the
-  # product refuses masked 3-d patches before touching the device (no GPU needed here)
+def test_masked_xcorr_rejects_unsupported_rank():
+  # correlation over 4 axes is refused before the device is touched (no GPU needed here)
   from sofima_b200 import flow_field as ff
-  monkeypatch.delenv('SOFIMA_EXPERIMENTAL_MASKED3D', raising=False)
   a = np.zeros((6, 6, 6), np.float32)
-  with pytest.raises(NotImplementedError):
-    ff.masked_xcorr(a, a, np.zeros(a.shape, bool), None, dim=3)
   with pytest.raises(NotImplementedError):
     ff.masked_xcorr(a, a, dim=4)

@@ -4,10 +4,8 @@ vectors of the reference's own run (tests/golden/coarse_golden.npz).
 
 The arithmetic of the kernel is the header csrc/tile_mesh_core.cuh, which
 tests/test_tile_mesh_host.py compiles for the host and checks bit for bit without a GPU.
-The kernel itself was written after this round's GPU time had run out, so its first run on
-hardware is this test: it executes in a child process (a fault there cannot disturb the
-CUDA context of the other tests) and is marked xfail(strict=False) until it has been seen
-to pass on a B200."""
+The kernel runs in a child process (a fault there cannot disturb the CUDA context of the other
+tests); it passed on a B200 at the end of round 1 (GPUTEST_r01: xpassed)."""
 import os
 import subprocess
 import sys
@@ -47,7 +45,6 @@ np.savez(sys.argv[3], **out)
 '''
 
 
-@pytest.mark.xfail(strict=False, reason='first run of csrc/tile_mesh.cu on hardware')
 def test_tile_mesh_matches_reference_run(tmp_path):
   import torch
   if not torch.cuda.is_available():
