@@ -41,7 +41,9 @@ struct sofima_ctx {
     bool valid = false;
     const void* img[2] = {nullptr, nullptr};
     int dtype = 0, h[2] = {0, 0}, w[2] = {0, 0}, pw[2] = {0, 0}, L = 0;
-    float2* spec[2] = {nullptr, nullptr};    // [nxs][h][L / 2 + 1]
+    int pitch = 0;                           // float2 per cached row (L / 2 + 1 rounded up to 8)
+    int nslots[2] = {0, 0};                  // distinct x starts per image
+    float2* spec[2] = {nullptr, nullptr};    // [nxs][h][pitch]
     const int* xindex[2] = {nullptr, nullptr};  // [w]: x start -> slot, -1 = not cached
     const float2* fix = nullptr;             // [3][L / 2 + 1]: rect(pre), rect(post), W(post)
   } rowcache;

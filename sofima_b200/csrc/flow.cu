@@ -1150,6 +1150,7 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       rcv.xindex[i] = rcache.xindex[i];
       rcv.h[i] = rcache.h[i];
     }
+    rcv.pitch = rcache.pitch;
     rcv.fix = rcache.fix;
     void* mb = nullptr;
     if ((rc = scratch(ctx, "flow.rc_meta", sizeof(int4) * 2 * B, &mb))) return rc;
@@ -1283,6 +1284,187 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
       SOFIMA_CHECK_LAUNCH(ctx);
     }
   }
+  return SOFIMA_OK;
+}
+
+}  // namespace flow
+}  // namespace sofima
+
+#include "flow_fused.cuh"
+
+namespace sofima {
+namespace flow {
+
+template <int N2, int NG>
+static int launch_pair_fused(sofima_ctx* ctx, int grid, const Problem& P, const float2* tw,
+                             const RowCacheView& rc, float2* slots, int upitch, float scale,
+                             const PeakParams& pp, PairPeaks* recs, int mode,
+                             const unsigned* bitmap, const int* fixlist, const int* nfix,
+                             float* out_peaks) {
+  const size_t smem = FusedDims<N2, NG>::smem_bytes;
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(pair_fused<N2, NG>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_fused<N2, NG><<<grid, FusedDims<N2, NG>::NT, smem, ctx->stream>>>(
+      P, tw, rc, slots, upitch, scale, pp, recs, mode, bitmap, fixlist, nfix, out_peaks);
+  return SOFIMA_OK;
+}
+
+#define SOFIMA_FUSED_N2_SWITCH(n2, CALL) \
+  switch (n2) {                          \
+    case 8: CALL(8); break;              \
+    case 10: CALL(10); break;            \
+    case 12: CALL(12); break;            \
+    case 15: CALL(15); break;            \
+    case 16: CALL(16); break;            \
+    case 20: CALL(20); break;            \
+    default: break;                      \
+  }
+
+// Whole batch through the fused kernel (flow_fused.cuh).  *handled = false: the batch is not
+// eligible (no row cache for these images, masks, unequal / long transforms) and nothing was
+// launched -- the caller takes the three-kernel path.
+static int run_fused(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
+                     const void* post_img, const int32_t* pre_starts,
+                     const int32_t* post_starts, long long B, const PeakParams& pp,
+                     float* out_peaks, bool* handled) {
+  *handled = false;
+  // Opt-in (SOFIMA_FLOW_FUSED=1).  Measured on a B200 (profiles/flow_fused_ab_r2.json): the
+  // fused kernel is bit-identical to the three-kernel path and removes its HBM round trips,
+  // but one pair per SM leaves 15-20 dependent warps to hide every latency, and the pipeline
+  // is bound by instruction issue, not by HBM: 8.8 ms vs 5.05 ms per 9801 pairs.
+  const char* fe = getenv("SOFIMA_FLOW_FUSED");
+  if (!fe || fe[0] != '1') return SOFIMA_OK;
+  if (p->ndim != 2 || B > INT32_MAX) return SOFIMA_OK;
+  Problem P;
+  memset(&P, 0, sizeof(P));
+  P.dtype = p->img_dtype;
+  const void* datas[2] = {pre_img, post_img};
+  const int64_t* shapes[2] = {p->pre_shape, p->post_shape};
+  const int32_t* patches[2] = {p->pre_patch, p->post_patch};
+  for (int i = 0; i < 2; ++i) {
+    P.img[i].data = datas[i];
+    P.img[i].h = (int)shapes[i][0];
+    P.img[i].w = (int)shapes[i][1];
+    P.img[i].ph = patches[i][0];
+    P.img[i].pw = patches[i][1];
+  }
+  P.starts[0] = pre_starts;
+  P.starts[1] = post_starts;
+  P.sy = p->pre_patch[0] + p->post_patch[0] - 1;
+  P.sx = p->pre_patch[1] + p->post_patch[1] - 1;
+  P.PY = p->pre_patch[0] > p->post_patch[0] ? p->pre_patch[0] : p->post_patch[0];
+  const int Ly = next_fast_len(P.sy), Lx = next_fast_len(P.sx);
+  P.nkx = Lx / 2 + 1;
+  P.nslots = 2;
+  P.has_mean = p->has_mean;
+  P.mean = p->mean;
+  P.b0 = 0;
+  P.nb = (int)B;
+  int n2 = 0;
+  if (Lx != Ly || !fast_n2(Lx, &n2) || n2 > 20) return SOFIMA_OK;
+  for (int i = 0; i < 2; ++i)
+    if (2 * P.img[i].ph > Lx || 2 * P.img[i].pw > Lx) return SOFIMA_OK;
+  if (2 * pp.ry + 1 > P.sy || 2 * pp.rx + 1 > P.sx) return SOFIMA_OK;  // run_peaks reports it
+  const sofima_ctx::RowCache& rcache = ctx->rowcache;
+  bool cached = rcache.valid && rcache.L == Lx && rcache.dtype == P.dtype;
+  for (int i = 0; i < 2 && cached; ++i)
+    cached = rcache.img[i] == P.img[i].data && rcache.h[i] == P.img[i].h &&
+             rcache.w[i] == P.img[i].w && rcache.pw[i] == P.img[i].pw;
+  if (!cached) return SOFIMA_OK;
+
+  int rc;
+  FftPlan Fx;
+  if ((rc = make_plan(ctx, Lx, &Fx))) return rc;
+  RowCacheView rcv;
+  memset(&rcv, 0, sizeof(rcv));
+  for (int i = 0; i < 2; ++i) {
+    rcv.spec[i] = rcache.spec[i];
+    rcv.xindex[i] = rcache.xindex[i];
+    rcv.h[i] = rcache.h[i];
+  }
+  rcv.pitch = rcache.pitch;
+  rcv.fix = rcache.fix;
+  void *mb = nullptr, *means = nullptr, *slots = nullptr, *recs = nullptr, *bm = nullptr,
+       *fix = nullptr;
+  if ((rc = scratch(ctx, "flow.rc_meta", sizeof(int4) * 2 * B, &mb))) return rc;
+  rcv.meta = static_cast<const int4*>(mb);
+  const bool dc_mean = !p->has_mean && P.dtype == SOFIMA_U8;
+  if (!p->has_mean && !dc_mean) {
+    if ((rc = scratch(ctx, "flow.means", sizeof(MeanPartial) * 2 * kMeanGroups * B, &means)))
+      return rc;
+    P.parts = static_cast<const MeanPartial*>(means);
+    for (long long b0 = 0; b0 < B; b0 += 65535) {
+      Problem Q = P;
+      Q.b0 = b0;
+      Q.nb = (int)((B - b0 < 65535) ? (B - b0) : 65535);
+      LaunchTimer timer(ctx, "flow_mean");
+      patch_mean_kernel<<<dim3(Q.nb, 2, kMeanGroups), kThreads, 0, ctx->stream>>>(
+          Q, (MeanPartial*)means);
+      SOFIMA_CHECK_LAUNCH(ctx);
+    }
+  }
+  {
+    LaunchTimer timer(ctx, "flow_mean");
+    const unsigned int mblocks = (unsigned int)ceil_div<long long>(2 * B * 32, 256);
+    if (dc_mean)
+      rowcache_meta_kernel<true><<<mblocks, 256, 0, ctx->stream>>>(P, rcv, B, (int4*)mb);
+    else
+      rowcache_meta_kernel<false><<<mblocks, 256, 0, ctx->stream>>>(P, rcv, B, (int4*)mb);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  const int upitch = (P.nkx + 7) & ~7;
+  int grid = ctx->num_sms;
+  if ((long long)grid > B) grid = (int)B;
+  const int fix_grid = grid < 8 ? grid : 8;
+  const size_t words = ((size_t)P.sy * P.sx + 31) / 32;
+  if ((rc = scratch(ctx, "flow.fused_slots",
+                    sizeof(float2) * (size_t)ctx->num_sms * P.sy * upitch, &slots))) return rc;
+  if ((rc = scratch(ctx, "flow.fused_recs", sizeof(PairPeaks) * (size_t)B, &recs))) return rc;
+  if ((rc = scratch(ctx, "flow.bitmap", sizeof(unsigned) * words, &bm))) return rc;
+  if ((rc = scratch(ctx, "flow.fused_fix", sizeof(int) * ((size_t)B + 1), &fix))) return rc;
+  int* nfix = static_cast<int*>(fix);
+  int* fixlist = nfix + 1;
+  SOFIMA_CUDA(ctx, cudaMemsetAsync(bm, 0, sizeof(unsigned) * words, ctx->stream));
+  SOFIMA_CUDA(ctx, cudaMemsetAsync(nfix, 0, sizeof(int), ctx->stream));
+  const float scale = (float)(1.0 / ((double)Lx * (double)Ly));
+  int ng = 3;  // thread groups per block (flow_fused.cuh)
+  if (const char* e = getenv("SOFIMA_FLOW_FUSED_GROUPS")) ng = atoi(e) == 4 ? 4 : 3;
+  {
+    LaunchTimer timer(ctx, "flow_fused");
+#define CALL(N)                                                                               \
+  rc = ng == 4 ? launch_pair_fused<N, 4>(ctx, grid, P, Fx.tw, rcv, (float2*)slots, upitch,    \
+                                         scale, pp, (PairPeaks*)recs, 0, nullptr, nullptr,    \
+                                         nullptr, nullptr)                                    \
+               : launch_pair_fused<N, 3>(ctx, grid, P, Fx.tw, rcv, (float2*)slots, upitch,    \
+                                         scale, pp, (PairPeaks*)recs, 0, nullptr, nullptr,    \
+                                         nullptr, nullptr)
+    SOFIMA_FUSED_N2_SWITCH(n2, CALL)
+#undef CALL
+    if (rc) return rc;
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  {
+    LaunchTimer timer(ctx, "flow_fused_select");
+    const unsigned nblk = (unsigned)ceil_div<long long>(B, 256);
+    fused_bitmap_kernel<<<nblk, 256, 0, ctx->stream>>>((const PairPeaks*)recs, B, (unsigned*)bm);
+    SOFIMA_CHECK_LAUNCH(ctx);
+    fused_finalize_kernel<<<nblk, 256, 0, ctx->stream>>>((const PairPeaks*)recs, B, pp,
+                                                         (const unsigned*)bm, out_peaks, fixlist,
+                                                         nfix);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  {
+    LaunchTimer timer(ctx, "flow_fused_fixup");
+#define CALL(N)                                                                               \
+  rc = launch_pair_fused<N, 3>(ctx, fix_grid, P, Fx.tw, rcv, (float2*)slots, upitch, scale,   \
+                               pp, (PairPeaks*)recs, 1, (const unsigned*)bm, fixlist, nfix,   \
+                               out_peaks)
+    SOFIMA_FUSED_N2_SWITCH(n2, CALL)
+#undef CALL
+    if (rc) return rc;
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  *handled = true;
   return SOFIMA_OK;
 }
 
@@ -1610,7 +1792,8 @@ int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const v
   const int32_t* xs[2] = {pre_xstarts, post_xstarts};
   const int ns[2] = {n_pre, n_post};
   size_t need = 0;
-  for (int i = 0; i < 2; ++i) need += (size_t)ns[i] * shapes[i][0] * nkx * sizeof(float2);
+  const int pitch = (nkx + 7) & ~7;  // rows start 64-byte aligned (TMA: 16-byte strides)
+  for (int i = 0; i < 2; ++i) need += (size_t)ns[i] * shapes[i][0] * pitch * sizeof(float2);
   size_t have = 0;
   for (const char* nm : {"flow.rowcache0", "flow.rowcache1"}) {
     auto it = ctx->scratch.find(nm);
@@ -1628,6 +1811,8 @@ int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const v
   sofima_ctx::RowCache c;
   c.dtype = p->img_dtype;
   c.L = Lx;
+  c.pitch = pitch;
+  for (int i = 0; i < 2; ++i) c.nslots[i] = ns[i];
   std::vector<int> table;
   std::vector<float2> fix((size_t)3 * nkx);
   const bool fix_ready = ctx->rowfix_key[0] == Lx && ctx->rowfix_key[1] == pws[0] &&
@@ -1647,7 +1832,7 @@ int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const v
                                {"flow.rowcache0", "flow.rowcache1"}};
     if ((rc = scratch(ctx, names[0][i], sizeof(int) * w, &tb))) return rc;
     if ((rc = scratch(ctx, names[1][i], sizeof(int) * ns[i], &xb))) return rc;
-    if ((rc = scratch(ctx, names[2][i], (size_t)ns[i] * h * nkx * sizeof(float2), &sb))) return rc;
+    if ((rc = scratch(ctx, names[2][i], (size_t)ns[i] * h * pitch * sizeof(float2), &sb))) return rc;
     SOFIMA_CUDA(ctx, cudaMemcpyAsync(tb, table.data(), sizeof(int) * w, cudaMemcpyHostToDevice,
                                      ctx->stream));
     SOFIMA_CUDA(ctx, cudaMemcpyAsync(xb, xs[i], sizeof(int) * ns[i], cudaMemcpyHostToDevice,
@@ -1658,6 +1843,7 @@ int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const v
     RowSpecJob J;
     J.data = datas[i]; J.dtype = p->img_dtype; J.h = h; J.w = w; J.pw = pw;
     J.xstarts = static_cast<const int*>(xb);
+    J.pitch = pitch;
     {
       LaunchTimer timer(ctx, "flow_rowspec");
 #define CALL(N) launch_rowspec_fast<N>(ctx, J, ns[i], Fx.tw, c.spec[i])
@@ -1729,6 +1915,12 @@ int sofima_xcorr_peaks(sofima_ctx* ctx, const sofima_xcorr_params* p, const void
   DeviceGuard guard(ctx->device);
   flow::PeakParams pp;
   flow::peak_params(p, &pp);
+  if (p->ndim == 2 && !pre_mask && !post_mask) {
+    bool handled = false;
+    rc = flow::run_fused(ctx, p, pre_img, post_img, pre_starts, post_starts, batch, pp,
+                         out_peaks, &handled);
+    if (rc || handled) return rc;
+  }
   const size_t img_elems = (size_t)pp.sz * pp.sy * pp.sx;
   void* images = nullptr;
   if ((rc = scratch(ctx, "flow.images", sizeof(float) * (size_t)batch * img_elems, &images)))

@@ -188,6 +188,7 @@ struct RowSpecJob {
   const void* data;
   int dtype, h, w, pw;
   const int* xstarts;  // [slots] device
+  int pitch;           // float2 elements per cached row (>= L / 2 + 1, a multiple of 8)
 };
 
 template <int N2, int TR, bool HALF>
@@ -251,7 +252,8 @@ rowspec_fast(RowSpecJob J, const float2* __restrict__ tw, float2* __restrict__ o
     for (int k2 = 0; k2 < N2; ++k2) xs[f * L + k1 + kN1 * k2] = bq[k2];
   }
   __syncthreads();
-  float2* ob = out + (size_t)blockIdx.y * nrows * NKX;
+  const int pitch = J.pitch;
+  float2* ob = out + (size_t)blockIdx.y * nrows * pitch;
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int f = warp; f < TR; f += NT / 32) {
@@ -261,19 +263,20 @@ rowspec_fast(RowSpecJob J, const float2* __restrict__ tw, float2* __restrict__ o
       for (int k = lane; k < NKX; k += 32) {
         const float2 a = xs[f * L + k];
         const float2 c = xs[f * L + (k == 0 ? 0 : L - k)];
-        ob[(size_t)y * NKX + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+        ob[(size_t)y * pitch + k] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
         if (two)
-          ob[(size_t)(y + 1) * NKX + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+          ob[(size_t)(y + 1) * pitch + k] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
       }
     }
   }
 }
 
 struct RowCacheView {
-  const float2* spec[2];
+  const float2* spec[2];  // [slot][h][pitch]
   const int* xindex[2];
   const float2* fix;  // [3][nkx]
   int h[2];
+  int pitch;          // float2 elements per cached row
   const int4* meta;   // [B][2]: {first cached row (lo, hi), mean bits, slot valid}
 };
 
@@ -297,8 +300,8 @@ __global__ void rowcache_meta_kernel(Problem P, RowCacheView RC, long long B, in
   float mean;
   if (DC_MEAN) {
     float s = 0.f;
-    const float2* col0 = RC.spec[sl] + first * P.nkx;
-    for (int y = lane; y < I.ph; y += 32) s += __ldg(&col0[(long long)y * P.nkx]).x;
+    const float2* col0 = RC.spec[sl] + first * RC.pitch;
+    for (int y = lane; y < I.ph; y += 32) s += __ldg(&col0[(long long)y * RC.pitch]).x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     mean = __fdiv_rn(s, (float)(I.ph * I.pw));
@@ -353,8 +356,8 @@ cols_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict__ T
     const int rows = P.img[sl].ph;
     const int4 m = meta2[sl];
     const long long row0 = ((long long)m.y << 32) | (unsigned int)m.x;
-    const long long cbase = row0 * P.nkx + k0 + c;
-    const long long cstep = sl == 0 ? P.nkx : -(long long)P.nkx;
+    const long long cbase = row0 * RC.pitch + k0 + c;
+    const long long cstep = sl == 0 ? RC.pitch : -(long long)RC.pitch;
 #pragma unroll
     for (int n1 = 0; n1 < NLOAD; ++n1) {
       const int y = N2 * n1 + r;

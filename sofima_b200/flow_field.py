@@ -395,7 +395,16 @@ class _FlowJob:
     patch_offset = patch_offset.astype(int)
     step_arr = np.array(step).reshape((1, -1))
 
-    self.batches = list(_batches(oyx, self.batch_size))
+    # Within a reference batch the ORDER of the patch pairs is free (the batch-coupled
+    # second-peak rule, flow_field.py:263-265, depends on the set only), so every batch is
+    # walked column-major: consecutive pairs then share 3/4 of their image rows at the same
+    # x start, which is what the fused kernel's row-spectra reads want to find in L2.
+    # `scatter` writes by position, so the flow field is unaffected.
+    self.batches = []
+    for pos in _batches(oyx, self.batch_size):
+      if nd == 2 and pos.shape[0] > 1:
+        pos = pos[np.lexsort((pos[:, 0], pos[:, 1]))]
+      self.batches.append(pos)
     pre_all, post_all, self.tg_all, self.po_all = [], [], [], []
     for pos_zyx in self.batches:
       real = pos_zyx.shape[0]
