@@ -47,6 +47,8 @@ struct sofima_ctx {
     const int* xindex[2] = {nullptr, nullptr};  // [w]: x start -> slot, -1 = not cached
     const float2* fix = nullptr;             // [3][L / 2 + 1]: rect(pre), rect(post), W(post)
   } rowcache;
+  // (L, pw, K, delta mask) of the twiddle digit tables "flow.tc_tab*" (flow_rowspec_tc.cuh)
+  int tc_tab_key[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
   int rowfix_key[3] = {0, 0, 0};  // (L, pw pre, pw post) of the table in scratch "flow.rc_fix"
 };
 

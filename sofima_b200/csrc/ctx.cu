@@ -109,6 +109,7 @@ int sofima_ctx_trim(sofima_ctx* ctx, int64_t keep_bytes) {
   SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->rowcache.valid = false;  // its spectra live in scratch buffers
   ctx->rowfix_key[0] = 0;
+  ctx->tc_tab_key[0][0] = ctx->tc_tab_key[1][0] = 0;
   for (auto it = ctx->scratch.begin(); it != ctx->scratch.end();) {
     if (it->second.ptr && (int64_t)it->second.bytes > keep_bytes) {
       SOFIMA_CUDA(ctx, cudaFree(it->second.ptr));

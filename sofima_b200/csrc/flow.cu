@@ -1291,6 +1291,7 @@ static int run_xcorr(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
 }  // namespace sofima
 
 #include "flow_fused.cuh"
+#include "flow_rowspec_tc.cuh"
 
 namespace sofima {
 namespace flow {
@@ -1762,6 +1763,157 @@ static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, cons
 }  // namespace flow
 }  // namespace sofima
 
+namespace sofima {
+namespace flow {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+            cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Twiddle digits of one transform length / patch width for rowspec_tc_kernel:
+// [ndelta][nchunks][kTcN x K] s8 in the MMA's no-swizzle K-major layout
+// (flow_rowspec_tc.cuh); matrix row x' of the table for `delta` is pixel x' - delta.
+static std::vector<int8_t> rowspec_tc_table(int L, int pw, int K, int nkx, int nchunks,
+                                            const std::vector<int>& deltas) {
+  std::vector<int8_t> tab(deltas.size() * (size_t)nchunks * kTcN * K, 0);
+  const size_t lbo = 128, sbo = 128 * (size_t)(K / 16);
+  // digits of every twiddle exp(-2 pi i m / L), m < L
+  std::vector<int8_t> dig((size_t)L * 8);
+  for (int m = 0; m < L; ++m) {
+    const double ph = -2.0 * M_PI * (double)m / (double)L;
+    for (int reim = 0; reim < 2; ++reim) {
+      long long T = llround((reim == 0 ? cos(ph) : sin(ph)) * 134217728.0);  // 2^27
+      int d[4];
+      for (int i = 3; i >= 1; --i) {
+        const long long r = ((T + 64) % 128 + 128) % 128 - 64;  // balanced digit in [-64, 63]
+        d[i] = (int)r;
+        T = (T - r) / 128;
+      }
+      d[0] = (int)T;  // |d0| <= 64 (+1 from a carry)
+      for (int i = 0; i < 4; ++i) dig[(size_t)m * 8 + reim * 4 + i] = (int8_t)d[i];
+    }
+  }
+  for (size_t di = 0; di < deltas.size(); ++di) {
+    for (int c = 0; c < nchunks; ++c) {
+      int8_t* t = tab.data() + (di * nchunks + c) * (size_t)kTcN * K;
+      for (int n = 0; n < kTcN; ++n) {
+        const int bin = c * kTcBins + n / 8;
+        if (bin >= nkx) continue;
+        for (int x = 0; x < pw; ++x) {
+          const int xp = x + deltas[di];
+          const int m = (int)((long long)x * bin % L);
+          t[(n / 8) * sbo + (xp / 16) * lbo + (n % 8) * 16 + (xp % 16)] = dig[(size_t)m * 8 + n % 8];
+        }
+      }
+    }
+  }
+  return tab;
+}
+
+// Row spectra of one image on the tensor cores.  *done = false: not eligible (dtype, image
+// pitch, patch width, no driver entry point) -- the caller runs rowspec_fast instead.
+static int rowspec_tc(sofima_ctx* ctx, int which, const void* img, int dtype, int h, int w,
+                      int pw, int L, const int32_t* xstarts_host, const int* xstarts_dev,
+                      int nslots, int pitch, float2* out, bool* done) {
+  *done = false;
+  if (const char* e = getenv("SOFIMA_FLOW_ROWSPEC_TC"))
+    if (e[0] == '0') return SOFIMA_OK;
+  if (dtype != SOFIMA_U8 || (w % 16) != 0 || ((uintptr_t)img & 15) != 0 || nslots < 1 || h < 1)
+    return SOFIMA_OK;
+  // distinct misalignments of the x starts and the slots of each
+  std::vector<int> deltas, didx(nslots);
+  for (int j = 0; j < nslots; ++j) {
+    const int d = xstarts_host[j] & 15;
+    size_t k = 0;
+    while (k < deltas.size() && deltas[k] != d) ++k;
+    if (k == deltas.size()) deltas.push_back(d);
+    didx[j] = (int)k;
+  }
+  int dmax = 0, dmask = 0;
+  for (int d : deltas) { dmax = d > dmax ? d : dmax; dmask |= 1 << d; }
+  const int K = (dmax + pw + 31) & ~31;
+  const int nd = (int)deltas.size();
+  if (K > kTcMaxK) return SOFIMA_OK;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return SOFIMA_OK;
+  const int nkx = L / 2 + 1;
+  const int nchunks = (nkx + kTcBins - 1) / kTcBins;
+  if (nd * nchunks > ctx->num_sms) return SOFIMA_OK;
+  // digit tables, cached per (L, pw, K, set of deltas) and image slot
+  char name[64];
+  snprintf(name, sizeof(name), "flow.tc_tab%d", which);
+  void *tab = nullptr, *dsl = nullptr;
+  const size_t tbytes = (size_t)nd * nchunks * kTcN * K;
+  int rc;
+  if ((rc = scratch(ctx, name, tbytes, &tab))) return rc;
+  int* key = ctx->tc_tab_key[which];
+  if (key[0] != L || key[1] != pw || key[2] != K || key[3] != dmask) {
+    const std::vector<int8_t> host = rowspec_tc_table(L, pw, K, nkx, nchunks, deltas);
+    SOFIMA_CUDA(ctx, cudaMemcpyAsync(tab, host.data(), tbytes, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    key[0] = L; key[1] = pw; key[2] = K; key[3] = dmask;
+  }
+  // [nd + 1] offsets, then the slot indices grouped by delta
+  std::vector<int> dslots(nd + 1 + nslots, 0);
+  for (int j = 0; j < nslots; ++j) dslots[didx[j] + 1]++;
+  for (int k = 0; k < nd; ++k) dslots[k + 1] += dslots[k];
+  {
+    std::vector<int> fill(dslots.begin(), dslots.begin() + nd);
+    for (int j = 0; j < nslots; ++j) dslots[nd + 1 + fill[didx[j]]++] = j;
+  }
+  snprintf(name, sizeof(name), "flow.tc_dslots%d", which);
+  if ((rc = scratch(ctx, name, sizeof(int) * dslots.size(), &dsl))) return rc;
+  SOFIMA_CUDA(ctx, cudaMemcpyAsync(dsl, dslots.data(), sizeof(int) * dslots.size(),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+  SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `dslots` goes out of scope
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+  const cuuint64_t strides[1] = {(cuuint64_t)w};
+  const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows}, es[2] = {1, 1};
+  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(img), dims,
+                          strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return SOFIMA_OK;  // odd geometry: plain path
+  RowSpecTcJob J;
+  J.h = h; J.nslots = nslots; J.pitch = pitch; J.nkx = nkx; J.K = K; J.nchunks = nchunks;
+  J.ndelta = nd;
+  J.xstarts = xstarts_dev;
+  J.dslots = static_cast<const int*>(dsl);
+  J.btab = static_cast<const int8_t*>(tab);
+  // > half of the SM's shared memory: one block per SM (a block owns all 512 TMEM columns)
+  const size_t smem = kTcSmemBytes;
+  SOFIMA_CUDA(ctx, cudaFuncSetAttribute(rowspec_tc_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ncombos = nd * nchunks;
+  const int grid = (ctx->num_sms / ncombos) * ncombos;
+  {
+    LaunchTimer timer(ctx, "flow_rowspec");
+    rowspec_tc_kernel<<<grid, kTcThreads, smem, ctx->stream>>>(map, J, out);
+    SOFIMA_CHECK_LAUNCH(ctx);
+  }
+  *done = true;
+  return SOFIMA_OK;
+}
+
+}  // namespace flow
+}  // namespace sofima
+
 extern "C" {
 
 int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
@@ -1844,7 +1996,11 @@ int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const v
     J.data = datas[i]; J.dtype = p->img_dtype; J.h = h; J.w = w; J.pw = pw;
     J.xstarts = static_cast<const int*>(xb);
     J.pitch = pitch;
-    {
+    bool tc_done = false;
+    if ((rc = rowspec_tc(ctx, i, datas[i], p->img_dtype, h, w, pw, Lx, xs[i], J.xstarts, ns[i],
+                         pitch, c.spec[i], &tc_done)))
+      return rc;
+    if (!tc_done) {
       LaunchTimer timer(ctx, "flow_rowspec");
 #define CALL(N) launch_rowspec_fast<N>(ctx, J, ns[i], Fx.tw, c.spec[i])
       SOFIMA_N2_SWITCH(n2x, CALL)

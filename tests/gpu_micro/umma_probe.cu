@@ -98,7 +98,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 template <int N, int K, int A_MODE>
 __global__ void __launch_bounds__(128)
 gemm_i8_probe(const uint8_t* __restrict__ A, int lda, const int8_t* __restrict__ B,
-              int32_t* __restrict__ D, const __grid_constant__ CUtensorMap amap) {
+              int32_t* __restrict__ D, const __grid_constant__ CUtensorMap amap, int xt) {
   constexpr int KC = K / 16;  // 16-byte chunks along K
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                 // 128 * K bytes
@@ -142,7 +142,7 @@ gemm_i8_probe(const uint8_t* __restrict__ A, int lda, const int8_t* __restrict__
     if (A_MODE == 1) {
       mbar_expect_tx(&bar_tma, 128 * K);
       for (int kb = 0; kb < K / 32; ++kb)  // box kb: image columns [32 kb, 32 kb + 32), rows 0..127
-        tma_load_2d(sA + kb * 128 * 32, &amap, kb * 32, 0, &bar_tma);
+        tma_load_2d(sA + kb * 128 * 32, &amap, xt + kb * 32, 0, &bar_tma);
       mbar_wait(&bar_tma, 0);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -231,7 +231,7 @@ static EncodeTiled get_encode() {
 
 template <int N, int K, int A_MODE>
 static int run_gemm(const char* name, EncodeTiled enc) {
-  const int W = 512, H = 128;  // A is a window of a [H][W] uint8 image starting at column 40
+  const int W = getenv("PROBE_W") ? atoi(getenv("PROBE_W")) : 512, H = 128;  // A is a window of a [H][W] uint8 image starting at column 40
   std::vector<uint8_t> img((size_t)H * W);
   std::vector<int8_t> b((size_t)N * K);
   srand(1234 + N + K);
@@ -253,7 +253,7 @@ static int run_gemm(const char* name, EncodeTiled enc) {
     cuuint32_t box[2] = {32, 128}, es[2] = {1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dimg, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     getenv("PROBE_L2_128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("%s: FAIL (encode %d)\n", name, (int)r); return 1; }
   }
   const size_t smem = 128 * K + N * K;
@@ -261,12 +261,13 @@ static int run_gemm(const char* name, EncodeTiled enc) {
                           (int)smem));
   // A_MODE 1 box coordinates are relative to column 0: shift the image pointer view instead
   CUtensorMap m2 = map;
-  gemm_i8_probe<N, K, A_MODE><<<1, 128, smem>>>(dimg + (A_MODE == 0 ? x0 : 0), W, db, dd, m2);
+  const int xt = getenv("PROBE_X0") ? atoi(getenv("PROBE_X0")) : 0;
+  gemm_i8_probe<N, K, A_MODE><<<1, 128, smem>>>(dimg + (A_MODE == 0 ? x0 : 0), W, db, dd, m2, xt);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s: FAIL (%s)\n", name, cudaGetErrorString(e)); return 1; }
   std::vector<int32_t> d(128 * N);
   CK(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
-  const int xa = A_MODE == 0 ? x0 : 0;  // mode 1 reads columns [0, K) of the image
+  const int xa = A_MODE == 0 ? x0 : xt;  // mode 1 reads columns [xt, xt + K) of the image
   long bad = 0;
   for (int r = 0; r < 128; ++r)
     for (int n = 0; n < N; ++n) {
