@@ -1897,7 +1897,10 @@ static int rowspec_tc(sofima_ctx* ctx, int which, const void* img, int dtype, in
   J.dslots = static_cast<const int*>(dsl);
   J.btab = static_cast<const int8_t*>(tab);
   // > half of the SM's shared memory: one block per SM (a block owns all 512 TMEM columns)
-  const size_t smem = kTcSmemBytes;
+  // (more than half of an SM's shared memory for the usual K: one block per SM, which owns
+  // all 512 TMEM columns)
+  const size_t smem = tc_smem_bytes(K);
+  if (smem > 220 * 1024) return SOFIMA_OK;
   SOFIMA_CUDA(ctx, cudaFuncSetAttribute(rowspec_tc_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ncombos = nd * nchunks;

@@ -39,8 +39,11 @@ constexpr int kTcMaxK = 256;
 constexpr int kTcOutPitch = kTcBins + 2; // float2 per staged output row (16-byte aligned rows)
 constexpr int kTcEpiWarps = 8;           // two per TMEM lane quarter, 12 bins each
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
-constexpr size_t kTcSmemBytes = 2 * (size_t)kTcRows * kTcMaxK + (size_t)kTcN * kTcMaxK +
-                                2 * (size_t)kTcRows * kTcOutPitch * sizeof(float2);
+constexpr int kTcStages = 4;             // A tiles in flight (TMA runs up to 4 items ahead)
+__host__ __device__ constexpr size_t tc_smem_bytes(int K) {
+  return (size_t)kTcStages * kTcRows * K + (size_t)kTcN * K +
+         2 * (size_t)kTcRows * kTcOutPitch * sizeof(float2);
+}
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -101,10 +104,11 @@ rowspec_tc_kernel(const __grid_constant__ CUtensorMap imap, const RowSpecTcJob J
                   float2* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   const int K = J.K;
-  uint8_t* sA[2] = {tc_smem, tc_smem + kTcRows * kTcMaxK};
-  uint8_t* sB = tc_smem + 2 * kTcRows * kTcMaxK;
-  float2* sOut = reinterpret_cast<float2*>(sB + kTcN * kTcMaxK);  // [2][128][kTcOutPitch]
-  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2], bar_b;
+  // [kTcStages] A tiles of 128 x K bytes (K / 32 swizzled boxes of 4 KB each), B, output tiles
+  uint8_t* sB = tc_smem + kTcStages * kTcRows * K;
+  float2* sOut = reinterpret_cast<float2*>(sB + kTcN * K);  // [2][128][kTcOutPitch]
+  __shared__ __align__(8) uint64_t bar_full[kTcStages], bar_empty[kTcStages], bar_tfull[2],
+      bar_tempty[2], bar_b;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -117,9 +121,11 @@ rowspec_tc_kernel(const __grid_constant__ CUtensorMap imap, const RowSpecTcJob J
   const int nitems = (__ldg(&J.dslots[di + 1]) - __ldg(&J.dslots[di])) * ntiles;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kTcStages; ++s) {
       tc_mbar_init(&bar_full[s], 1);
       tc_mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc_mbar_init(&bar_tfull[s], 1);
       tc_mbar_init(&bar_tempty[s], 32 * kTcEpiWarps);
     }
@@ -147,8 +153,8 @@ rowspec_tc_kernel(const __grid_constant__ CUtensorMap imap, const RowSpecTcJob J
             "r"(tc_smem_u32(&bar_b)) : "memory");
       int n = 0;
       for (int it = worker; it < nitems; it += nworkers, ++n) {
-        const int s = n & 1;
-        tc_mbar_wait(&bar_empty[s], ((n >> 1) & 1) ^ 1);
+        const int s = n % kTcStages;
+        tc_mbar_wait(&bar_empty[s], ((n / kTcStages) & 1) ^ 1);
         const int si = it / ntiles, tile = it - si * ntiles;
         const int xa = __ldg(&J.xstarts[__ldg(&myslots[si])]) & ~15;
         tc_mbar_expect_tx(&bar_full[s], (uint32_t)(kTcRows * K));
@@ -156,7 +162,8 @@ rowspec_tc_kernel(const __grid_constant__ CUtensorMap imap, const RowSpecTcJob J
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
               "[%0], [%1, {%2, %3}], [%4];"
-              ::"r"(tc_smem_u32(sA[s] + kb * kTcRows * 32)), "l"(&imap), "r"(xa + kb * 32),
+              ::"r"(tc_smem_u32(tc_smem + (s * K + kb * 32) * kTcRows)), "l"(&imap),
+                "r"(xa + kb * 32),
                 "r"(tile * kTcRows), "r"(tc_smem_u32(&bar_full[s])) : "memory");
       }
     }
@@ -167,13 +174,14 @@ rowspec_tc_kernel(const __grid_constant__ CUtensorMap imap, const RowSpecTcJob J
       const uint32_t lbo = 128, sbo = 128u * (uint32_t)(K / 16);
       int n = 0;
       for (int it = worker; it < nitems; it += nworkers, ++n) {
-        const int s = n & 1;
-        tc_mbar_wait(&bar_full[s], (n >> 1) & 1);
-        tc_mbar_wait(&bar_tempty[s], ((n >> 1) & 1) ^ 1);
+        const int s = n % kTcStages, a = n & 1;
+        tc_mbar_wait(&bar_full[s], (n / kTcStages) & 1);
+        tc_mbar_wait(&bar_tempty[a], ((n >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dcol = tbase + (uint32_t)(s * 256);
+        const uint32_t dcol = tbase + (uint32_t)(a * 256);
         for (int kb = 0; kb < K / 32; ++kb) {
-          const uint64_t da = tc_desc(tc_smem_u32(sA[s] + kb * kTcRows * 32), 16, 256, 6);
+          const uint64_t da =
+              tc_desc(tc_smem_u32(tc_smem + (s * K + kb * 32) * kTcRows), 16, 256, 6);
           const uint64_t db = tc_desc(tc_smem_u32(sB) + kb * 2 * lbo, lbo, sbo, 0);
           asm volatile(
               "{ .reg .pred p; setp.ne.b32 p, %4, 0; "
@@ -184,7 +192,7 @@ rowspec_tc_kernel(const __grid_constant__ CUtensorMap imap, const RowSpecTcJob J
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                      ::"r"(tc_smem_u32(&bar_empty[s])) : "memory");
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     ::"r"(tc_smem_u32(&bar_tfull[s])) : "memory");
+                     ::"r"(tc_smem_u32(&bar_tfull[a])) : "memory");
       }
     }
   } else {
