@@ -138,3 +138,18 @@ def ndimage_warp(image, coord_map: np.ndarray, stride: Sequence[float],
   if labels_back is not None:
     warped = labels_back[warped]
   return warped
+
+
+def warp_subvolume(image, image_box, coord_map, map_box, stride, out_box, interpolation=None,
+                   offset: float = 0.0, parallelism: int = 1):
+  """Warps a [n, z, y, x] subvolume through an xy inverse coordinate map (warp.py:58-186).
+
+  The reference evaluates this with OpenCV's fixed-point `remap` (Lanczos / linear /
+  nearest on CV_16SC2 maps); a CUDA restatement of those interpolation tables is not part of
+  this backend yet, so the call fails loudly instead of falling back to the CPU.  Use
+  `ndimage_warp` (bit-exact against SciPy) for map-based rendering on the device.
+  """
+  del image, image_box, coord_map, map_box, stride, out_box, interpolation, offset, parallelism
+  raise NotImplementedError(
+      'warp_subvolume (OpenCV remap semantics) is not built in the CUDA backend; '
+      'ndimage_warp renders through the same kind of map on the device')

@@ -202,8 +202,26 @@ def test_decorator_chunk_functions():  # decorators/flow_test.py:55-88
   vol = _volume(2, 200)[0].astype(np.float32)
   f = dflow.optim_flow(vol[0], vol[1], (80, 80), (40, 40), batch_size=8)
   assert f.shape == (4, 4, 4) and (f[0] == -3).all() and (f[1] == 2).all()
-  with pytest.raises((ImportError, NotImplementedError)):
-    dflow.OptimFlow()
+  # the decorator classes over the in-memory stand-in for TensorStore
+  # (decorators/flow_test.py:55-88: MeshRelaxFlowFilter == the direct call; :90-118 OptimFlow)
+  from sofima_b200.compat import volume
+  data = rng.uniform(size=(3, 3, 3, 3)).astype('float32')
+  fargs = {'k0': 0.1, 'k': 0.1, 'dt': 0.001, 'gamma': 0.0, 'stride': (1, 1, 1),
+           'num_iters': 1000, 'max_iters': 50_000, 'stop_v_max': 0.001, 'dt_max': 1000}
+  store = volume.ArrayStore(data, ['fc', 'fz', 'fy', 'fx'])
+  vc = dflow.MeshRelaxFlowFilter(min_chunksize=store.shape, **fargs).decorate(store)
+  np.testing.assert_equal(vc[...].read().result(), dflow.mesh_relax_flow(data, **fargs))
+  # OptimFlow: (x, y, z) stores, one flow field per section, padded to the image grid
+  xyz = np.ascontiguousarray(np.stack([vol[0], vol[0]], axis=-1).transpose(1, 0, 2))
+  fixed = np.ascontiguousarray(np.stack([vol[1], vol[1]], axis=-1).transpose(1, 0, 2))
+  dec = dflow.OptimFlow(fixed_spec={'array': fixed, 'labels': ['x', 'y', 'z']},
+                        image_dims=('x', 'y'), patch_size=(80, 80), step_size=(40, 40),
+                        batch_size=8).decorate(volume.ArrayStore(xyz, ['x', 'y', 'z']))
+  out = dec[...].read().result()
+  assert out.shape == (4, 1, 5, 5, 2)
+  np.testing.assert_array_equal(out[:, 0, 1:5, 1:5, 0], f)   # pad_left = 80 // 40 // 2 = 1
+  np.testing.assert_array_equal(out[..., 0], out[..., 1])
+  assert np.isnan(out[:, :, 0]).all() and np.isnan(out[:, :, :, 0]).all()
 
 
 def test_masked_xcorr_rejects_unsupported_rank():
@@ -212,3 +230,55 @@ def test_masked_xcorr_rejects_unsupported_rank():
   a = np.zeros((6, 6, 6), np.float32)
   with pytest.raises(NotImplementedError):
     ff.masked_xcorr(a, a, dim=4)
+
+
+# ---- decorator classes (ports of /root/reference/decorators/flow_test.py:25-118 on the
+# in-memory stand-in for TensorStore, compat/volume.py) -------------------------------
+
+
+def test_clean_flow_filter_decorator():
+  from sofima_b200.compat import volume
+  from sofima_b200.decorators import flow as decorators
+  rng = np.random.default_rng(0)
+  data = rng.uniform(size=(5, 3, 3, 3)).astype('float32')
+  f = volume.ArrayStore(data, ['fc', 'fz', 'fy', 'fx'])
+  filter_args = {'min_peak_sharpness': 1.6, 'min_peak_ratio': 1.4, 'max_magnitude': 20,
+                 'max_deviation': 2}
+  vc = decorators.CleanFlowFilter(min_chunksize=f.shape, **filter_args).decorate(f)
+  assert vc.shape == (3, 3, 3, 3) and vc.domain.labels == ('fc', 'fz', 'fy', 'fx')
+  res = vc[...].read().result()
+  np.testing.assert_equal(res, decorators.clean_flow(data, **filter_args))
+
+
+def test_reconcile_flow_filter_decorator():
+  from sofima_b200.compat import volume
+  from sofima_b200.decorators import flow as decorators
+  rng = np.random.default_rng(1)
+  data = rng.uniform(size=(3, 3, 3, 3)).astype('float32')   # decorators/flow_test.py:120-147
+  f = volume.ArrayStore(data, ['fc', 'fz', 'fy', 'fx'])
+  filter_args = {'max_gradient': 2.0, 'max_deviation': 2, 'min_patch_size': 20}
+  vc = decorators.ReconcileFlowFilter(min_chunksize=f.shape, **filter_args).decorate(f)
+  res = vc[...].read().result()
+  np.testing.assert_equal(res, decorators.reconcile_flow(data, **filter_args))
+  # a sub-domain read is cut out of the same whole-array chunk
+  np.testing.assert_equal(vc[:, :, 1:3, 0:2].read().result(), res[:, :, 1:3, 0:2])
+
+
+def test_optim_flow_decorator_geometry():
+  from sofima_b200.compat import volume
+  from sofima_b200.decorators import flow as decorators
+  img = volume.ArrayStore(np.zeros((3, 3), np.float32), ['x', 'y'])
+  dec = decorators.OptimFlow(fixed_spec=img, image_dims=('x', 'y')).decorate(img)
+  assert dec.domain.labels == ('fc', 'fz', 'fy', 'fx')
+  # 200 x 160 (x, y) images over 3 sections: padded flow grid + trailing non-image dim
+  vol = volume.ArrayStore(np.zeros((200, 160, 3), np.float32), ['x', 'y', 'z'])
+  dec = decorators.OptimFlow(fixed_spec={'array': np.zeros((200, 160, 3), np.float32),
+                                         'labels': ['x', 'y', 'z']},
+                             image_dims=('x', 'y'), patch_size=(80, 80), step_size=(40, 40),
+                             batch_size=8).decorate(vol)
+  assert dec.domain.labels == ('fc', 'fz', 'fy', 'fx', 'z')
+  assert dec.shape == (4, 1, 4, 5, 3)   # ceil((160-80+1)/40) + 1 = 4, ceil((200-80+1)/40) + 1 = 5
+  with pytest.raises(ValueError):
+    decorators.OptimFlow(fixed_spec=img, image_dims=('x', 'y')).decorate(vol)
+  with pytest.raises(ValueError):
+    decorators.OptimFlow(fixed_spec=vol, image_dims=('x',)).decorate(vol)
