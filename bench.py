@@ -876,6 +876,8 @@ def run_ours(args):
     line.update(result)
     emit(line)
   if world > 1:
+    from sofima_b200 import mesh_sharded as _ms
+    _ms.clear_shard_cache()  # peer mappings go before the process group does
     dist.destroy_process_group()
 
 

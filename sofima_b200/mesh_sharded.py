@@ -52,7 +52,12 @@ def partition_rows(ny: int, nranks: int, align: int = ROW_ALIGN) -> list[tuple[i
 
 
 class ShardedMesh:
-  """Rank-local slab of a row-sharded mesh, with the solver state on the device."""
+  """Rank-local slab of a row-sharded mesh, with the solver state on the device.
+
+  Creating one is expensive (a peer-mapped allocation, an IPC handle exchange and two
+  barriers, ~50 ms): `relax_mesh_sharded` keeps the object of every (slab shape, group) and
+  only reloads the state for the next solve (`load`).
+  """
 
   def __init__(self, x_local, prev_local, config: mesh_lib.IntegrationConfig, group=None):
     import torch
@@ -61,16 +66,12 @@ class ShardedMesh:
     self.group = group
     self.rank = dist.get_rank(group) if dist.is_initialized() else 0
     self.nranks = dist.get_world_size(group) if dist.is_initialized() else 1
-    self.config = config
     self.ctx = _native.Context.get(torch.cuda.current_device())
-    self.like = x_local
-    x = mesh_lib._to_device(x_local, self.ctx, copy=False)
-    prev = None if prev_local is None else mesh_lib._to_device(prev_local, self.ctx, copy=False)
-    if x.ndim != 4 or x.shape[0] != 2:
-      raise ValueError(f'expected a [2, z, y, x] slab, got {tuple(x.shape)}')
-    self.shape = tuple(x.shape)
-    self.pod = mesh_lib._config_pod(config, 0)
-    shp = _native.MeshShape(2, x.shape[1], 1, x.shape[2], x.shape[3])
+    shape = tuple(x_local.shape)
+    if len(shape) != 4 or shape[0] != 2:
+      raise ValueError(f'expected a [2, z, y, x] slab, got {shape}')
+    self.shape = shape
+    shp = _native.MeshShape(2, shape[1], 1, shape[2], shape[3])
     lib = _native.lib()
     self.ctx.bind_stream()
     h = ctypes.c_void_p()
@@ -86,19 +87,31 @@ class ShardedMesh:
     else:
       allb = blob.raw
     _native.check(self.ctx.handle, lib.sofima_shard_connect(h, allb))
-    _native.check(self.ctx.handle, lib.sofima_shard_set_state(
-        h, x.data_ptr(), None, None if prev is None else prev.data_ptr()))
-    nodes = torch.tensor([x.shape[1] * x.shape[2] * x.shape[3]], dtype=torch.int64,
-                         device=x.device)
+    nodes = torch.tensor([shape[1] * shape[2] * shape[3]], dtype=torch.int64,
+                         device=torch.device('cuda', self.ctx.device))
     if self.nranks > 1:
       dist.all_reduce(nodes, group=group)
     self.global_nodes = int(nodes.item())
+    self.load(x_local, prev_local, config)
+
+  def load(self, x_local, prev_local, config: mesh_lib.IntegrationConfig):
+    """(Re)loads positions (velocities = 0) and the fixed target of the slab."""
+    if tuple(x_local.shape) != self.shape:
+      raise ValueError(f'slab shape {tuple(x_local.shape)} != {self.shape}')
+    self.config = config
+    self.like = x_local
+    self.pod = mesh_lib._config_pod(config, 0)
+    x = mesh_lib._to_device(x_local, self.ctx, copy=False)
+    prev = None if prev_local is None else mesh_lib._to_device(prev_local, self.ctx, copy=False)
+    self.ctx.bind_stream()
+    _native.check(self.ctx.handle, _native.lib().sofima_shard_set_state(
+        self.handle, x.data_ptr(), None, None if prev is None else prev.data_ptr()))
     self._join()
 
   def _join(self):
     """All ranks' queued work is complete (chunk boundaries only)."""
     self._torch.cuda.synchronize()
-    if self.nranks > 1:
+    if self.nranks > 1 and self._dist.is_initialized():
       self._dist.barrier(group=self.group)
 
   def run(self, dt: float, alpha: float, cap: float):
@@ -165,7 +178,7 @@ def relax_mesh_sharded(x_local, prev_local, config: mesh_lib.IntegrationConfig, 
     if config.cap_scale <= 1:
       raise ValueError('The scaling factor for the force cap has to be larger '
                        'than 1 when the initial and final cap are different.')
-  shard = ShardedMesh(x_local, prev_local, config, group)
+  shard = _cached_shard(x_local, prev_local, config, group)
   t, dt, alpha, cap, e_kin = 0, config.dt, config.alpha, config.start_cap, []
   try:
     while t < config.max_iters:
@@ -182,6 +195,51 @@ def relax_mesh_sharded(x_local, prev_local, config: mesh_lib.IntegrationConfig, 
         cap = min(np.float32(cap) * np.float32(config.cap_scale),
                   np.float32(config.final_cap))
     x = shard.state()[0]
-  finally:
-    shard.close()
+  except Exception:
+    _drop_shard(shard)  # never reuse a shard whose ranks may be out of step
+    raise
   return mesh_lib._from_device(x, x_local), e_kin, t
+
+
+# Shards of recent solves, keyed by (device, slab shape, group): all ranks of a group call
+# relax_mesh_sharded in lockstep, so they hit or miss the cache together.
+_SHARDS: dict = {}
+_MAX_SHARDS = 4
+
+
+def _cached_shard(x_local, prev_local, config, group) -> ShardedMesh:
+  import torch
+  key = (torch.cuda.current_device(), tuple(x_local.shape), id(group))
+  shard = _SHARDS.get(key)
+  if shard is not None and getattr(shard, 'handle', None):
+    shard.load(x_local, prev_local, config)
+    return shard
+  while len(_SHARDS) >= _MAX_SHARDS:
+    _SHARDS.pop(next(iter(_SHARDS))).close()
+  shard = _SHARDS[key] = ShardedMesh(x_local, prev_local, config, group)
+  return shard
+
+
+def _drop_shard(shard: ShardedMesh):
+  for k, v in list(_SHARDS.items()):
+    if v is shard:
+      del _SHARDS[k]
+  try:
+    shard.close()
+  except Exception:  # pylint: disable=broad-except
+    pass
+
+
+def clear_shard_cache():
+  """Frees the peer-mapped buffers of all cached shards (collective: call on every rank,
+  before the process group is destroyed)."""
+  for shard in list(_SHARDS.values()):
+    try:
+      shard.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+  _SHARDS.clear()
+
+
+import atexit  # pylint: disable=wrong-import-position
+atexit.register(clear_shard_cache)  # while the CUDA context and the library are still alive

@@ -61,6 +61,7 @@ def main():
     print(json.dumps(dict(world=world, shape=shape, iters=iters, steps=t, ok=bool(ok),
                           max_abs_err=err, sharded_s=t_sharded, single_gpu_s=t_single,
                           us_per_step_sharded=t_sharded / t * 1e6)))
+  mesh_sharded.clear_shard_cache()
   dist.destroy_process_group()
   if not ok:
     sys.exit(1)
