@@ -318,6 +318,30 @@ int sofima_warp_image(sofima_ctx* ctx, int dim, const void* image, int img_dtype
                       const double* stride, int order, void* out,
                       const int64_t* out_shape);
 
+/* ------------------------------------------------------------------------- *
+ *  Flow-field post-filters (reference: flow_utils.py, map_utils.py)
+ * ------------------------------------------------------------------------- */
+
+/* flow_utils.clean_flow (flow_utils.py:37-78).  flow: [nc][z][y][x] fp32 with nc = dim
+ * (vectors) or dim + 2 (vectors, peak sharpness, peak ratio); out: [dim][z][y][x], rejected
+ * vectors NaN.  max_magnitude / max_deviation <= 0 disable the respective test. */
+int sofima_clean_flow(sofima_ctx* ctx, const float* flow, int nc, int dim, const int64_t* zyx,
+                      float min_peak_ratio, float min_peak_sharpness, float max_magnitude,
+                      float max_deviation, float* out);
+
+/* flow_utils.reconcile_flows (flow_utils.py:81-135).  out: [nc][z][y][x] (nc = 2 or 3), on
+ * entry the most preferred estimate, filtered in place; others: `nothers` further estimates
+ * in order of decreasing preference (host array of device pointers). */
+int sofima_reconcile_flows(sofima_ctx* ctx, float* out, const float* const* others, int nothers,
+                           int nc, const int64_t* zyx, float max_gradient, float max_deviation,
+                           int min_patch_size, float min_delta_z);
+
+/* map_utils.mask_irregular (map_utils.py:737-786).  coord_map: [2][ny][nx] relative map,
+ * masked nodes set to NaN in place; out_mask: [ny][nx] bytes (1 = masked). */
+int sofima_mask_irregular(sofima_ctx* ctx, float* coord_map, int64_t ny, int64_t nx,
+                          const double* stride_xy, double frac, double max_frac,
+                          int dilation_iters, uint8_t* out_mask);
+
 #ifdef __cplusplus
 }
 #endif

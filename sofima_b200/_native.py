@@ -31,6 +31,7 @@ SOURCES = {
     'mesh.cu': ['-fmad=false'],
     'tile_mesh.cu': ['-fmad=false'],  # fp32 operation order of mesh.py / stitch_rigid.py
     'flow.cu': [],
+    'flowfilt.cu': ['-fmad=false'],  # fp32 comparisons exactly as NumPy evaluates them
     'warp.cu': ['-fmad=false'],  # float64 arithmetic identical to SciPy's
 }
 
@@ -216,6 +217,16 @@ _PROTOS = {
     'sofima_xcorr_images': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_int64, _vp]),
+    'sofima_clean_flow': (ctypes.c_int, [
+        _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_float,
+        ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
+    'sofima_reconcile_flows': (ctypes.c_int, [
+        _vp, _vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_int64), ctypes.c_float, ctypes.c_float, ctypes.c_int,
+        ctypes.c_float]),
+    'sofima_mask_irregular': (ctypes.c_int, [
+        _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_double),
+        ctypes.c_double, ctypes.c_double, ctypes.c_int, _vp]),
     'sofima_batched_peaks': (ctypes.c_int, [
         _vp, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64,
         ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_float,

@@ -4,17 +4,64 @@
   clean_flow        flow_utils.py:36-78
   reconcile_flows   flow_utils.py:81-135
 
-These are small NumPy / SciPy filters in the reference as well (they sit between the
-hot-path calls); they run on the host here too and are pinned by golden
-vectors from the reference module (tests/golden/flow_utils_golden.npz).
+These are small NumPy / SciPy filters in the reference (they sit between the hot-path calls,
+SURVEY 8 f-4).  Two residencies, one result: NumPy arrays are filtered on the host exactly as
+upstream does; CUDA tensors are filtered by the kernels of csrc/flowfilt.cu and stay on the
+device, so that a section loop (EstimateMissingFlow, RelaxMesh) never leaves the GPU between
+two hot-path calls.  Both are pinned on golden vectors from the reference module
+(tests/golden/flow_utils_golden.npz; tests/test_flowfilt_gpu.py requires them to be equal).
 """
 
 from __future__ import annotations
 
+import ctypes
 from typing import Sequence
 
 import numpy as np
 from scipy import ndimage
+
+
+def _is_cuda(a) -> bool:
+  return type(a).__module__.startswith('torch') and a.is_cuda
+
+
+def _device_call(like):
+  from . import _native
+  ctx = _native.Context.get(like.device.index)
+  ctx.bind_stream()
+  return _native, ctx
+
+
+def _clean_flow_device(flow, min_peak_ratio, min_peak_sharpness, max_magnitude, max_deviation,
+                       dim):
+  import torch
+  native, ctx = _device_call(flow)
+  f = flow.to(torch.float32).contiguous()
+  if f.ndim != 4:
+    raise ValueError('device clean_flow takes a [c, z, y, x] tensor')
+  out = torch.empty((dim,) + tuple(f.shape[1:]), dtype=torch.float32, device=f.device)
+  rc = native.lib().sofima_clean_flow(
+      ctx.handle, f.data_ptr(), int(f.shape[0]), int(dim), (ctypes.c_int64 * 3)(*f.shape[1:]),
+      float(min_peak_ratio), float(min_peak_sharpness), float(max_magnitude),
+      float(max_deviation), out.data_ptr())
+  native.check(ctx.handle, rc)
+  return out
+
+
+def _reconcile_flows_device(flows, max_gradient, max_deviation, min_patch_size, min_delta_z):
+  import torch
+  native, ctx = _device_call(flows[0])
+  out = flows[0].to(torch.float32).contiguous().clone()
+  if out.ndim != 4 or out.shape[0] not in (2, 3):
+    raise ValueError('device reconcile_flows takes [2 or 3, z, y, x] tensors')
+  others = [f.to(out.device, torch.float32).contiguous() for f in flows[1:]]
+  ptrs = (ctypes.c_void_p * max(1, len(others)))(*[o.data_ptr() for o in others])
+  rc = native.lib().sofima_reconcile_flows(
+      ctx.handle, out.data_ptr(), ptrs, len(others), int(out.shape[0]),
+      (ctypes.c_int64 * 3)(*out.shape[1:]), float(max_gradient), float(max_deviation),
+      int(min_patch_size), float(min_delta_z))
+  native.check(ctx.handle, rc)
+  return out
 
 
 def apply_mask(flow: np.ndarray, mask: np.ndarray):
@@ -49,6 +96,9 @@ def clean_flow(flow: np.ndarray, min_peak_ratio: float, min_peak_sharpness: floa
   """
   assert dim in (2, 3)
   assert dim <= flow.shape[0] <= dim + 2
+  if _is_cuda(flow):
+    return _clean_flow_device(flow, min_peak_ratio, min_peak_sharpness, max_magnitude,
+                              max_deviation, dim)
   vec = flow[:dim, ...]
   with np.errstate(invalid='ignore'):
     if flow.shape[0] == dim + 2:
@@ -82,6 +132,9 @@ def reconcile_flows(flows: Sequence[np.ndarray], max_gradient: float, max_deviat
   Returns:
     [c, z, y, x] reconciled flow
   """
+  if _is_cuda(flows[0]):
+    return _reconcile_flows_device(flows, max_gradient, max_deviation, min_patch_size,
+                                   min_delta_z)
   out = flows[0].copy()
   nch = out.shape[0]
   assert nch in (2, 3)

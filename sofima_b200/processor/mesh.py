@@ -59,16 +59,32 @@ def mask_irregular(coord_map: np.ndarray, stride: Sequence[float], frac: float,
   3x3 structuring element.  Bad nodes are set to NaN in place; returns the mask.
   """
   assert coord_map.ndim == 3 and coord_map.shape[0] == 2
-  sx, sy = float(stride[0]), float(stride[1])
+  if type(coord_map).__module__.startswith('torch') and coord_map.is_cuda:
+    # device-resident map: csrc/flowfilt.cu (same result, the mesh never leaves the GPU)
+    import ctypes
+    import torch
+    from .. import _native
+    if coord_map.dtype != torch.float32 or not coord_map.is_contiguous():
+      raise ValueError('device mask_irregular needs a contiguous float32 [2, y, x] tensor')
+    ctx = _native.Context.get(coord_map.device.index)
+    ctx.bind_stream()
+    bad = torch.empty(coord_map.shape[1:], dtype=torch.uint8, device=coord_map.device)
+    rc = _native.lib().sofima_mask_irregular(
+        ctx.handle, coord_map.data_ptr(), int(coord_map.shape[1]), int(coord_map.shape[2]),
+        (ctypes.c_double * 2)(float(stride[0]), float(stride[1])), float(frac),
+        float(2 - frac if max_frac is None else max_frac), int(dilation_iters), bad.data_ptr())
+    _native.check(ctx.handle, rc)
+    return bad.bool()
+  # as upstream: the stride (a NumPy scalar of the `stride` array) promotes the fp32
+  # differences to float64 before the comparisons
+  stride = np.asarray(stride)
+  stride_x, stride_y = stride
   hi = 2 - frac if max_frac is None else max_frac
-  gap_x = np.zeros(coord_map.shape[1:], coord_map.dtype)
-  gap_y = np.zeros(coord_map.shape[1:], coord_map.dtype)
-  gap_x[:, :-1] = np.diff(coord_map[0], axis=-1)
-  gap_y[:-1, :] = np.diff(coord_map[1], axis=-2)
-  gap_x += sx
-  gap_y += sy
+  diff_x = np.pad(np.diff(coord_map[0], axis=-1), [[0, 0], [0, 1]], mode='constant') + stride_x
+  diff_y = np.pad(np.diff(coord_map[1], axis=-2), [[0, 1], [0, 0]], mode='constant') + stride_y
   with np.errstate(invalid='ignore'):
-    bad = (gap_x < frac * sx) | (gap_y < frac * sy) | (gap_x > hi * sx) | (gap_y > hi * sy)
+    bad = (diff_x < frac * stride_x) | (diff_y < frac * stride_y)
+    bad |= (diff_x > hi * stride_x) | (diff_y > hi * stride_y)
   if dilation_iters > 0:
     bad = ndimage.binary_dilation(bad, ndimage.generate_binary_structure(2, 2),
                                   iterations=dilation_iters)
