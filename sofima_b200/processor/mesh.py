@@ -317,28 +317,38 @@ class RelaxMesh(compat.SubvolumeProcessor):
       apply_mask(x, mask)
     logging.info('Starting mesh relaxation with: %r', cfg)
 
-    x, e_kin, steps = mesh_lib.relax_mesh(x, prev, integration_config)
-    x = np.array(x)
-    first = x.copy()
-    folded = mask_irregular(x[:, 0], integration_config.stride, cfg.mesh_min_frac,
+    # The three solves and the irregularity tests between them run on device-resident
+    # tensors (mesh solver, csrc/flowfilt.cu mask_irregular): the mesh crosses PCIe once in
+    # each direction, not after every step as upstream (processor/mesh.py:462-471).
+    import torch
+    from .. import _native
+    dev = torch.device('cuda', _native.Context.get().device)
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    xd, pd = to_dev(x), to_dev(prev)
+    xd, e_kin, steps = mesh_lib.relax_mesh(xd, pd, integration_config)
+    first = xd.clone()
+    sec = xd[:, 0].contiguous()
+    folded = mask_irregular(sec, integration_config.stride, cfg.mesh_min_frac,
                             dilation_iters=5)
-    if not folded.any():
-      return x, e_kin, steps, SolutionStatus.REGULAR
+    if not bool(folded.any()):
+      return first.cpu().numpy(), e_kin, steps, SolutionStatus.REGULAR
+    xd[:, 0] = sec
 
     logging.info('Attempting relaxation with 10% k0.')
     # Pull a fresh mesh towards the first solution (which now has NaN around the
     # irregular nodes) with weak springs; if that is regular, solve again from it.
     start = self.maybe_update_init_state(np.zeros_like(x), prev, cfg.options)
     soft = dataclasses.replace(integration_config, k0=integration_config.k0 / 10.0)
-    x, _, prep_steps = mesh_lib.relax_mesh(start, x, soft)
-    x = np.array(x)
-    if mask_irregular(x[:, 0], integration_config.stride, cfg.mesh_min_frac).any():
-      return first, e_kin, steps + prep_steps, SolutionStatus.PREP_FAILED
+    xd, _, prep_steps = mesh_lib.relax_mesh(to_dev(start), xd, soft)
+    sec = xd[:, 0].contiguous()
+    if bool(mask_irregular(sec, integration_config.stride, cfg.mesh_min_frac).any()):
+      return first.cpu().numpy(), e_kin, steps + prep_steps, SolutionStatus.PREP_FAILED
+    xd[:, 0] = sec
 
     if mask is not None:
-      apply_mask(x, mask)
-    x, e_kin2, reg_steps = mesh_lib.relax_mesh(x, prev, integration_config)
-    return (np.array(x), e_kin2, steps + prep_steps + reg_steps,
+      xd[:, torch.from_numpy(np.ascontiguousarray(mask)).to(dev)] = float('nan')
+    xd, e_kin2, reg_steps = mesh_lib.relax_mesh(xd, pd, integration_config)
+    return (xd.cpu().numpy(), e_kin2, steps + prep_steps + reg_steps,
             SolutionStatus.REGULARIZED)
 
   def run_relaxation(self, bbox):
