@@ -474,10 +474,16 @@ class _FlowJob:
       cached = rc == _native.OK  # unsupported size / no memory: plain path
     try:
       for i in progress_fn(list(range(nb))):
+        # The 'edge' padding of the last batch (flow_field.py:614-618) repeats its final
+        # position: the copies have the same first peak as the original, so they add
+        # nothing to the batch's erase set (flow_field.py:263-265) and their rows are
+        # discarded -- only the real pairs are computed.  The masked path normalises with
+        # batch-wide maxima (flow_field.py:137, :151), which duplicates cannot change either.
+        real = self.batches[i].shape[0]
         rc = lib.sofima_xcorr_peaks(
             self.ctx.handle, ctypes.byref(params), pre_d.data_ptr(), post_d.data_ptr(),
             _ptr(pre_m), _ptr(post_m), self.starts_d[0, i].data_ptr(),
-            self.starts_d[1, i].data_ptr(), self.batch_size, out[i].data_ptr())
+            self.starts_d[1, i].data_ptr(), real, out[i].data_ptr())
         _native.check(self.ctx.handle, rc)
     finally:
       if cached:
