@@ -1783,6 +1783,39 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// Small integer tables (patch x starts, slot lists) travel to the device as kernel
+// arguments: a cudaMemcpyAsync from pageable memory synchronises the stream first, which
+// would serialise back-to-back flow_field calls on short strips (BASELINE config 2).
+struct SmallInts {
+  int v[240];
+};
+__global__ void upload_small_kernel(SmallInts s, int n, int* dst) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = s.v[i];
+}
+// table[x] = slot of x start x, -1 elsewhere
+__global__ void xindex_kernel(const int* __restrict__ xstarts, int n, int* __restrict__ table,
+                              int w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w) {
+    int slot = -1;
+    for (int j = 0; j < n; ++j) slot = xstarts[j] == i ? j : slot;
+    table[i] = slot;
+  }
+}
+static int upload_ints(sofima_ctx* ctx, const int* host, int n, int* dst) {
+  if (n <= 240) {
+    SmallInts s;
+    memcpy(s.v, host, sizeof(int) * n);
+    upload_small_kernel<<<1, 256, 0, ctx->stream>>>(s, n, dst);
+    SOFIMA_CHECK_LAUNCH(ctx);
+    return SOFIMA_OK;
+  }
+  SOFIMA_CUDA(ctx, cudaMemcpyAsync(dst, host, sizeof(int) * n, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+  SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller reuses `host`
+  return SOFIMA_OK;
+}
+
 // Twiddle digits of one transform length / patch width for rowspec_tc_kernel:
 // [ndelta][nchunks][kTcN x K] s8 in the MMA's no-swizzle K-major layout
 // (flow_rowspec_tc.cuh); matrix row x' of the table for `delta` is pixel x' - delta.
@@ -1877,9 +1910,8 @@ static int rowspec_tc(sofima_ctx* ctx, int which, const void* img, int dtype, in
   }
   snprintf(name, sizeof(name), "flow.tc_dslots%d", which);
   if ((rc = scratch(ctx, name, sizeof(int) * dslots.size(), &dsl))) return rc;
-  SOFIMA_CUDA(ctx, cudaMemcpyAsync(dsl, dslots.data(), sizeof(int) * dslots.size(),
-                                   cudaMemcpyHostToDevice, ctx->stream));
-  SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `dslots` goes out of scope
+  if ((rc = upload_ints(ctx, dslots.data(), (int)dslots.size(), static_cast<int*>(dsl))))
+    return rc;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
@@ -1988,11 +2020,10 @@ int sofima_xcorr_rowcache(sofima_ctx* ctx, const sofima_xcorr_params* p, const v
     if ((rc = scratch(ctx, names[0][i], sizeof(int) * w, &tb))) return rc;
     if ((rc = scratch(ctx, names[1][i], sizeof(int) * ns[i], &xb))) return rc;
     if ((rc = scratch(ctx, names[2][i], (size_t)ns[i] * h * pitch * sizeof(float2), &sb))) return rc;
-    SOFIMA_CUDA(ctx, cudaMemcpyAsync(tb, table.data(), sizeof(int) * w, cudaMemcpyHostToDevice,
-                                     ctx->stream));
-    SOFIMA_CUDA(ctx, cudaMemcpyAsync(xb, xs[i], sizeof(int) * ns[i], cudaMemcpyHostToDevice,
-                                     ctx->stream));
-    SOFIMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `table` is reused
+    if ((rc = upload_ints(ctx, xs[i], ns[i], static_cast<int*>(xb)))) return rc;
+    xindex_kernel<<<ceil_div(w, 256), 256, 0, ctx->stream>>>(static_cast<const int*>(xb), ns[i],
+                                                             static_cast<int*>(tb), w);
+    SOFIMA_CHECK_LAUNCH(ctx);
     c.xindex[i] = static_cast<const int*>(tb);
     c.spec[i] = static_cast<float2*>(sb);
     RowSpecJob J;

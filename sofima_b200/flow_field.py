@@ -41,6 +41,53 @@ def _is_tensor(a) -> bool:
   return type(a).__module__.startswith('torch')
 
 
+class _Staging(threading.local):
+  """Per-thread pinned arena for small host <-> device transfers.  Pinned allocations are
+  expensive (cudaHostAlloc), and pageable copies synchronise the stream; slices of one
+  grow-never arena cost nothing.  The arena is handed out front to back; when it is full
+  the stream is synchronised once and it starts over."""
+
+  CAP = 192 << 20
+
+  def __init__(self):
+    self.buf = None
+    self.off = 0
+
+  def take(self, nbytes: int):
+    torch = _torch()
+    if nbytes > self.CAP // 4:
+      return None
+    if self.buf is None:
+      self.buf = torch.empty(self.CAP, dtype=torch.uint8, pin_memory=True)
+    need = (nbytes + 255) & ~255
+    if self.off + need > self.CAP:
+      torch.cuda.synchronize()  # every transfer that used the arena has completed
+      self.off = 0
+    view = self.buf[self.off:self.off + nbytes]
+    self.off += need
+    return view
+
+
+_STAGING = _Staging()
+
+
+def _upload(a: np.ndarray, dev):
+  """Host array -> device without synchronising the stream: the array is staged in pinned
+  memory (one pass that also makes strided views contiguous) and copied asynchronously.  A
+  plain `.to(device)` of pageable memory waits for all work queued on the stream first,
+  which serialises back-to-back calls on short strips."""
+  torch = _torch()
+  src = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+  if src.is_contiguous() and src.is_pinned():
+    return src.to(dev, non_blocking=True)
+  raw = _STAGING.take(src.numel() * src.element_size())
+  if raw is None:  # large image: the synchronisation is amortised
+    return src.contiguous().to(dev)
+  stage = raw.view(src.dtype).view(src.shape)
+  stage.copy_(src)
+  return stage.to(dev, non_blocking=True)
+
+
 def _device_image(img, ctx):
   """uint8 or float32 contiguous CUDA tensor + SOFIMA dtype code."""
   torch = _torch()
@@ -53,7 +100,7 @@ def _device_image(img, ctx):
   a = np.asarray(img)
   if a.dtype != np.uint8:
     a = a.astype(np.float32)  # JAX computes in fp32 whatever the input dtype
-  return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+  return _upload(a, dev)
 
 
 def _device_mask(mask, ctx):
@@ -64,7 +111,7 @@ def _device_mask(mask, ctx):
   if _is_tensor(mask):
     return (mask.to(dev) != 0).to(torch.uint8).contiguous()
   m = np.ascontiguousarray(np.asarray(mask) != 0).view(np.uint8)
-  return torch.from_numpy(m).to(dev, non_blocking=True)
+  return _upload(m, dev)
 
 
 def _int3(vals, fill=0):
@@ -294,6 +341,7 @@ class JAXMaskedXCorrWithStatsCalculator:
   """
 
   non_spatial_flow_channels = 2  # peak sharpness, peak ratio
+  supports_async = True          # flow_field(..., _async=True) returns a handle
 
   def __init__(self, mean: float | None = None, peak_min_distance: float = 2,
                peak_radius: float = 5):
@@ -307,12 +355,15 @@ class JAXMaskedXCorrWithStatsCalculator:
                  post_patch_size=None, pre_targeting_field=None,
                  pre_targeting_step=None, post_targeting_field=None,
                  post_targeting_step=None,
-                 progress_fn: Callable[[list[T]], Iterator[T]] = _silent_fn):
+                 progress_fn: Callable[[list[T]], Iterator[T]] = _silent_fn,
+                 _async: bool = False):
     """Computes the flow field from post to pre (flow_field.py:474-712).
 
     Arguments and result are those of the reference.  Returns a float32 array
     [ndim + 2, *out_shape]; channel order x, y[, z], sharpness, peak ratio; NaN
-    where no flow was computed.
+    where no flow was computed.  (`_async=True`, used by stitch_elastic.compute_flow_map:
+    returns a handle whose `.result()` gives that array, so that many short calls can be
+    queued on the GPU before the first result is read back.)
     """
     assert pre_image.ndim == post_image.ndim
     nd = pre_image.ndim
@@ -356,7 +407,7 @@ class JAXMaskedXCorrWithStatsCalculator:
     oyx = np.array(np.where(selection_mask)).T
     logging.info('Starting flow estimation for %d patches.', oyx.shape[0])
     if oyx.shape[0] == 0:
-      return output
+      return _PendingFlow(None, None, output, ()) if _async else output
 
     ctx = _native.Context.get()
     pre_d = _device_image(pre_image, ctx)
@@ -368,9 +419,35 @@ class JAXMaskedXCorrWithStatsCalculator:
                       pre_targeting_step, post_targeting_field, post_targeting_step)
     peaks_d = job.run(pre_d, post_d, pre_m, post_m, self._mean, self._min_distance,
                       self._peak_radius, progress_fn)
-    job.scatter(peaks_d.cpu().numpy(), output)
-    logging.info('Flow field estimation complete.')
-    return output
+    pending = _PendingFlow(job, peaks_d, output, (pre_d, post_d, pre_m, post_m))
+    return pending if _async else pending.result()
+
+
+class _PendingFlow:
+  """Result of a queued flow_field call: the peak table is copied to pinned host memory
+  asynchronously; `result()` waits for it and scatters it into the flow field."""
+
+  def __init__(self, job, peaks_d, output, keep_alive):
+    self._job, self._output, self._keep = job, output, keep_alive
+    self._host = self._event = None
+    if job is not None:
+      torch = _torch()
+      raw = _STAGING.take(peaks_d.numel() * peaks_d.element_size())
+      if raw is None:
+        raw = torch.empty(peaks_d.numel() * peaks_d.element_size(), dtype=torch.uint8,
+                          pin_memory=True)
+      self._host = raw.view(peaks_d.dtype).view(peaks_d.shape)
+      self._host.copy_(peaks_d, non_blocking=True)
+      self._event = torch.cuda.Event()
+      self._event.record()
+
+  def result(self) -> np.ndarray:
+    if self._job is not None:
+      self._event.synchronize()
+      self._job.scatter(self._host.numpy(), self._output)
+      self._job = self._keep = None
+      logging.info('Flow field estimation complete.')
+    return self._output
 
 
 class _FlowJob:
@@ -433,7 +510,7 @@ class _FlowJob:
     starts_h = np.ascontiguousarray(
         np.stack([np.stack(pre_all), np.stack(post_all)]), dtype=np.int32)
     dev = torch.device('cuda', ctx.device)
-    self.starts_d = torch.from_numpy(starts_h).to(dev).contiguous()  # [2, nb, B, nd]
+    self.starts_d = _upload(starts_h, dev)  # [2, nb, B, nd]
     self.num_pairs = int(oyx.shape[0])
     # Distinct patch x starts (clamped like the kernels' dynamic_slice) per image, for
     # the shared row spectra (sofima_xcorr_rowcache).

@@ -76,7 +76,10 @@ def compute_flow_map(tile_map: Mapping[tuple[int, int], np.ndarray], offset_map:
   step = tuple(int(v) for v in stride)
   stride = np.asarray(step)
   pad = [patch_size[0] // 2 // step[0], patch_size[1] // 2 // step[1]]
-  flows, offsets = {}, {}
+  flows, offsets, pending = {}, {}, {}
+  # Every strip pair is queued on the GPU before the first flow field is read back: the
+  # strips are short (a few hundred patch pairs), and a host round trip per strip would cost
+  # more than the correlation itself.
   for y in range(ny_t - axis):
     for x in range(nx_t - (1 - axis)):
       if np.isnan(offset_map[0, y, x]):
@@ -100,12 +103,16 @@ def compute_flow_map(tile_map: Mapping[tuple[int, int], np.ndarray], offset_map:
       elif ortho < 0:
         pre_sel[axis] = slice(None, ortho)
         post_sel[axis] = slice(-ortho, None)
-      f = calc.flow_field(pre[tuple(pre_sel)], post[tuple(post_sel)],
-                          patch_size=tuple(patch_size), step=step, batch_size=batch_size)
-      # The inverse flow (post, pre) is -f: it is not computed separately.
-      flows[x, y] = np.pad(f, [[0, 0], [pad[0], pad[0] - 1], [pad[1], pad[1] - 1]],
-                           constant_values=np.nan)
+      kw = {'_async': True} if getattr(calc, 'supports_async', False) else {}
+      pending[x, y] = calc.flow_field(pre[tuple(pre_sel)], post[tuple(post_sel)],
+                                      patch_size=tuple(patch_size), step=step,
+                                      batch_size=batch_size, **kw)
       offsets[x, y] = (-overlap, ortho) if axis == 0 else (ortho, -overlap)
+  for key, handle in pending.items():
+    # The inverse flow (post, pre) is -f: it is not computed separately.
+    f = handle.result() if hasattr(handle, 'result') else handle
+    flows[key] = np.pad(f, [[0, 0], [pad[0], pad[0] - 1], [pad[1], pad[1] - 1]],
+                        constant_values=np.nan)
   return flows, offsets
 
 
