@@ -374,3 +374,81 @@ def test_masked_xcorr_3d_unequal_volumes(ff):
   got_m = ff.masked_xcorr(search, query, sm, None, dim=3)
   want_m = fo.masked_xcorr(search, query, sm, None, dim=3)
   np.testing.assert_allclose(got_m, want_m, rtol=0, atol=2e-4)
+
+
+# ---- Blackwell-specific paths: tensor-core row spectra, fused per-pair kernel ---------
+
+
+def _rowcache_case(seed=41, n=520):
+  rng = np.random.default_rng(seed)
+  base = ndi.gaussian_filter(rng.standard_normal((n + 40, n + 40)), 1.5)
+  base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+  pre = np.ascontiguousarray(base[20:20 + n - 8, 20:20 + n])     # width 520: 16-byte rows
+  post = np.ascontiguousarray(base[23:23 + n - 8, 16:16 + n])
+  return pre, post
+
+
+@pytest.mark.parametrize('patch,step', [(160, 40), (64, 24)])
+def test_tensor_core_row_spectra_match_fft_row_spectra(ff, monkeypatch, patch, step):
+  """rowspec_tc_kernel (TMA -> tcgen05.mma kind::i8 with base-128 twiddle digits, exact
+  integer DFT; x starts at 24 j exercise three different 16-byte misalignments) against
+  rowspec_fast (fp32 FFT on the CUDA cores) and against the oracle."""
+  pre, post = _rowcache_case()
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  kw = dict(patch_size=patch, step=step, batch_size=64)
+  monkeypatch.setenv('SOFIMA_FLOW_ROWSPEC_TC', '1')
+  tc = calc.flow_field(pre, post, **kw)
+  monkeypatch.setenv('SOFIMA_FLOW_ROWSPEC_TC', '0')
+  fft = calc.flow_field(pre, post, **kw)
+  np.testing.assert_array_equal(np.isnan(tc), np.isnan(fft))
+  np.testing.assert_array_equal(tc[:2], fft[:2])              # integer flow vectors
+  ok = np.isfinite(fft[2])
+  # the two row transforms differ by fp32 rounding only: compare min / peak absolutely
+  np.testing.assert_allclose(1 / tc[2][ok], 1 / fft[2][ok], rtol=0, atol=2e-6)
+  np.testing.assert_allclose(tc[3][ok], fft[3][ok], rtol=2e-4, atol=1e-6)
+  want = fo.MaskedXCorrWithStatsCalculator().flow_field(pre, post, **kw)
+  np.testing.assert_array_equal(tc[:2], want[:2])
+  assert np.isfinite(tc[0]).mean() > 0.9
+
+
+@pytest.mark.parametrize('groups', ['3', '4'])
+@pytest.mark.parametrize('patch,step,bs', [(160, 40, 16), (64, 16, 100)])
+def test_fused_pipeline_matches_three_kernel_path(ff, monkeypatch, groups, patch, step, bs):
+  """pair_fused (columns -> product -> inverse columns -> inverse rows -> peaks in one
+  persistent launch, SOFIMA_FLOW_FUSED=1) reproduces the three-kernel path BIT FOR BIT,
+  statistics channels included -- it executes the same codelets in the same order."""
+  pre, post = _rowcache_case(seed=43)
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  kw = dict(patch_size=patch, step=step, batch_size=bs)
+  monkeypatch.setenv('SOFIMA_FLOW_FUSED', '0')
+  three = calc.flow_field(pre, post, **kw)
+  monkeypatch.setenv('SOFIMA_FLOW_FUSED', '1')
+  monkeypatch.setenv('SOFIMA_FLOW_FUSED_GROUPS', groups)
+  from sofima_b200 import _native
+  ctx = _native.Context.get(0)
+  ctx.set_timing(True)
+  fused = calc.flow_field(pre, post, **kw)
+  rep = ctx.timing_report()
+  ctx.set_timing(False)
+  assert 'flow_fused' in rep and 'flow_cols' not in rep        # the fused kernel did run
+  np.testing.assert_array_equal(fused, three)
+  assert np.isfinite(fused[0]).mean() > 0.9
+
+
+def test_fused_pipeline_second_peak_rule(ff, monkeypatch):
+  """A periodic texture gives many local maxima above half the peak height; the fused
+  kernel's 32-candidate record and the exact fix-up pass must reproduce the batch-coupled
+  erase rule (flow_field.py:263-265) of the three-kernel path."""
+  y, x = np.mgrid[:400, :416]
+  rng = np.random.default_rng(7)
+  tex = (np.sin(2 * np.pi * x / 20.0) + np.sin(2 * np.pi * y / 24.0)) * 50 + 128
+  pre = np.clip(tex + rng.normal(0, 4, tex.shape), 0, 255).astype(np.uint8)
+  post = np.clip(np.roll(tex, (2, -3), (0, 1)) + rng.normal(0, 4, tex.shape), 0, 255).astype(np.uint8)
+  calc = ff.JAXMaskedXCorrWithStatsCalculator()
+  kw = dict(patch_size=160, step=40, batch_size=24)
+  monkeypatch.setenv('SOFIMA_FLOW_FUSED', '0')
+  three = calc.flow_field(pre, post, **kw)
+  monkeypatch.setenv('SOFIMA_FLOW_FUSED', '1')
+  fused = calc.flow_field(pre, post, **kw)
+  np.testing.assert_array_equal(fused, three)
+  assert (three[3][np.isfinite(three[3])] > 0).any()            # second peaks do exist
