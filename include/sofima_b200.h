@@ -235,7 +235,8 @@ int sofima_shard_destroy(sofima_mesh_shard* shard);
  *  Patch flow  (reference: flow_field.py)
  * ------------------------------------------------------------------------- */
 
-enum { SOFIMA_U8 = 0, SOFIMA_F32 = 1, SOFIMA_U16 = 2, SOFIMA_U32 = 3 /* warp only */ };
+enum { SOFIMA_U8 = 0, SOFIMA_F32 = 1, SOFIMA_U16 = 2, SOFIMA_U32 = 3 /* warp only */,
+       SOFIMA_I16 = 4 /* warp_subvolume only */ };
 
 typedef struct {
   int32_t ndim;            /* 2 or 3 */
@@ -317,6 +318,28 @@ int sofima_warp_image(sofima_ctx* ctx, int dim, const void* image, int img_dtype
                       const int64_t* map_shape, const double* offset,
                       const double* stride, int order, void* out,
                       const int64_t* out_shape);
+
+/* Replaces the per-pixel work of warp.warp_subvolume (warp.py:58-186): for every output
+ * pixel of every section, densify the xy coordinate map (scipy RegularGridInterpolator,
+ * linear with extrapolation, float64 -> float32; warp.py:144-153), quantise it like
+ * cv2.convertMaps to CV_16SC2 (warp.py:155-160) and sample all channels like cv2.remap with
+ * a zero constant border (warp.py:162-165).  Results are identical to scipy + OpenCV.
+ *   image: device [n][nz][ih][iw] (image_shape = those four), img_dtype SOFIMA_U8 | _U16 |
+ *          _I16 | _F32, or _U32 for any 4-byte integer with interpolation 0 (label ids)
+ *   abs_map: device float64 [2][nz][my][mx], x then y coordinate of every map node in
+ *            pixels of `image` (map_utils.to_absolute + box offsets, warp.py:123-126, done by
+ *            the caller in the map's own dtype; map_is_f64 tells whether that dtype was
+ *            float64 -- scipy evaluates the two cases in a different order)
+ *   grid_y [my], grid_x [mx]: device float64, node positions in output pixels
+ *            (warp.py:130-134), strictly ascending
+ *   skip: device [nz] or NULL; sections with skip[z] != 0 are left zero (warp.py:117-119)
+ *   interpolation: 0 nearest, 1 linear, 2 cubic, 3 lanczos (warp.py:33-40)
+ *   out: device [n][nz][oh][ow], same dtype as image */
+int sofima_warp_subvolume(sofima_ctx* ctx, const void* image, int img_dtype,
+                          const int64_t* image_shape, const double* abs_map, int map_is_f64,
+                          const double* grid_y, const double* grid_x, int64_t my, int64_t mx,
+                          const uint8_t* skip, int interpolation, void* out, int64_t oh,
+                          int64_t ow);
 
 /* ------------------------------------------------------------------------- *
  *  Flow-field post-filters (reference: flow_utils.py, map_utils.py)

@@ -33,6 +33,7 @@ SOURCES = {
     'flow.cu': [],
     'flowfilt.cu': ['-fmad=false'],  # fp32 comparisons exactly as NumPy evaluates them
     'warp.cu': ['-fmad=false'],  # float64 arithmetic identical to SciPy's
+    'warp_cv.cu': ['-fmad=false'],  # float arithmetic identical to SciPy's / OpenCV's
 }
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, 1, 2, 3, 4
@@ -211,6 +212,10 @@ _PROTOS = {
         _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), _vp,
         ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double),
         ctypes.POINTER(ctypes.c_double), ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64)]),
+    'sofima_warp_subvolume': (ctypes.c_int, [
+        _vp, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), _vp, ctypes.c_int, _vp, _vp,
+        ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int, _vp, ctypes.c_int64,
+        ctypes.c_int64]),
     'sofima_xcorr_rowcache': (ctypes.c_int, [
         _vp, ctypes.POINTER(XcorrParams), _vp, _vp, ctypes.POINTER(ctypes.c_int32),
         ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),

@@ -140,16 +140,126 @@ def ndimage_warp(image, coord_map: np.ndarray, stride: Sequence[float],
   return warped
 
 
+_INTERPOLATION = {'nearest': 0, 'linear': 1, 'cubic': 2, 'lanczos': 3}
+_CV_FLAGS = {0: 0, 1: 1, 2: 2, 4: 3}  # cv2.INTER_NEAREST / _LINEAR / _CUBIC / _LANCZOS4
+_SECTION_DTYPES = {np.dtype(np.uint8): 0, np.dtype(np.float32): 1, np.dtype(np.uint16): 2,
+                   np.dtype(np.int32): 3, np.dtype(np.uint32): 3, np.dtype(np.int16): 4}
+
+
+def _interpolation_code(interpolation) -> int:
+  """warp.py:33-40 (names) and the cv2 flag values the reference also accepts."""
+  if isinstance(interpolation, str):
+    return _INTERPOLATION[interpolation]  # KeyError for unknown names, like the reference
+  try:
+    return _CV_FLAGS[int(interpolation)]
+  except (KeyError, TypeError, ValueError):
+    raise ValueError(f'unknown interpolation {interpolation!r}') from None
+
+
 def warp_subvolume(image, image_box, coord_map, map_box, stride, out_box, interpolation=None,
                    offset: float = 0.0, parallelism: int = 1):
   """Warps a [n, z, y, x] subvolume through an xy inverse coordinate map (warp.py:58-186).
 
-  The reference evaluates this with OpenCV's fixed-point `remap` (Lanczos / linear /
-  nearest on CV_16SC2 maps); a CUDA restatement of those interpolation tables is not part of
-  this backend yet, so the call fails loudly instead of falling back to the CPU.  Use
-  `ndimage_warp` (bit-exact against SciPy) for map-based rendering on the device.
+  Args:
+    image: [n, z, y, x] data to warp (uint8, uint16, int16, float32; uint32 below 2**16 is
+      warped as uint16; uint64 is treated as segmentation and sampled nearest-neighbour on
+      contiguous ids); NumPy array or CUDA tensor
+    image_box: bounding box of `image` within the volume
+    coord_map: [2, z, y, x] relative xy coordinate map (source position of every node)
+    map_box: bounding box of `coord_map`
+    stride: image pixels per coordinate-map pixel
+    out_box: bounding box of the warped output
+    interpolation: 'nearest' | 'linear' | 'cubic' | 'lanczos' (or the cv2 flag); defaults to
+      Lanczos for images
+    offset: (deprecated upstream) shift applied to the map and its node positions
+    parallelism: accepted for compatibility (host threads in the reference)
+
+  Returns:
+    warped image covering `out_box`, [n, z, out_y, out_x]; values equal the reference's
+    scipy + OpenCV pipeline bit for bit (one CUDA kernel, csrc/warp_cv.cu).
   """
-  del image, image_box, coord_map, map_box, stride, out_box, interpolation, offset, parallelism
-  raise NotImplementedError(
-      'warp_subvolume (OpenCV remap semantics) is not built in the CUDA backend; '
-      'ndimage_warp renders through the same kind of map on the device')
+  del parallelism
+  torch = _mesh._torch()
+  is_tensor = _mesh._is_tensor(image)
+  if image.ndim != 4:
+    raise ValueError(f'expected an [n, z, y, x] image, got shape {tuple(image.shape)}')
+  labels_back = None
+  orig_dtype = None
+  if not is_tensor:
+    image = np.asarray(image)
+    orig_dtype = image.dtype
+    if image.dtype == np.uint64:  # warp.py:93-100
+      # Id 0 stays at index 0 whether or not it occurs, as labels.make_contiguous does.
+      ids = np.unique(np.append(image.ravel(), np.uint64(0)))
+      assert len(ids) < 2**31
+      image = np.searchsorted(ids, image).astype(np.int32)
+      labels_back, interpolation = ids, 'nearest'
+    elif image.dtype == np.uint32:  # warp.py:109-115
+      if image.size and image.max() >= 2**16:
+        raise ValueError('Image warping supported up to uint16 only. For segmentation '
+                         'data, use uint64.')
+      image = image.astype(np.uint16)
+    np_dtype = image.dtype
+  else:
+    np_dtype = np.dtype(str(image.dtype).replace('torch.', ''))
+    if np_dtype == np.uint32 or np_dtype == np.uint64:
+      raise NotImplementedError('pass uint32 / uint64 volumes as NumPy arrays (they are '
+                                'converted on the host like in the reference)')
+  code = 3 if interpolation is None else _interpolation_code(interpolation)
+  if np_dtype not in _SECTION_DTYPES:
+    raise NotImplementedError(f'image dtype {np_dtype} is not supported by the CUDA warp')
+  if _SECTION_DTYPES[np_dtype] == 3 and code != 0:
+    raise NotImplementedError('32-bit integer data is only warped nearest-neighbour '
+                              '(OpenCV has no other mode for it either)')
+
+  coord_map = np.asarray(coord_map)
+  if coord_map.ndim != 4 or coord_map.shape[0] != 2 or coord_map.shape[1] != image.shape[1]:
+    raise ValueError(f'coordinate map {coord_map.shape} does not match image '
+                     f'{tuple(image.shape)}')
+  if not np.issubdtype(coord_map.dtype, np.floating):
+    coord_map = coord_map.astype(np.float64)
+  if coord_map.shape[2] < 2 or coord_map.shape[3] < 2:
+    raise ValueError('The points in dimension 0 must have at least 2 points')  # as scipy
+  skipped = np.all(np.isnan(coord_map), axis=(0, 2, 3))  # warp.py:117-119
+  # Map nodes -> coordinates within `image` (warp.py:123-126), in the map's own dtype.
+  abs_map = _to_absolute(coord_map, (float(stride), float(stride)))
+  mstart = np.asarray(map_box.start)
+  abs_map += (mstart[:2] * stride - np.asarray(image_box.start)[:2] + offset).reshape(2, 1, 1, 1)
+  # Node positions within the output (warp.py:130-134).
+  ostart = np.asarray(out_box.start)
+  grid_y = (np.arange(coord_map.shape[2]) + mstart[1]) * stride - ostart[1] + offset
+  grid_x = (np.arange(coord_map.shape[3]) + mstart[0]) * stride - ostart[0] + offset
+  out_shape = (int(image.shape[0]), int(out_box.size[2]), int(out_box.size[1]),
+               int(out_box.size[0]))
+  if out_shape[1] != image.shape[1]:
+    raise ValueError(f'out_box has {out_shape[1]} sections, the image {image.shape[1]}')
+
+  dev = image.device.index if is_tensor and image.is_cuda else None
+  ctx = _native.Context.get(dev)
+  device = torch.device('cuda', ctx.device)
+  if is_tensor:
+    img_d = image.to(device).contiguous()
+  else:
+    img_d = torch.from_numpy(np.ascontiguousarray(image).view(np.uint8)).to(device)
+  host = np.concatenate([np.ascontiguousarray(abs_map, dtype=np.float64).ravel(),
+                         np.asarray(grid_y, np.float64), np.asarray(grid_x, np.float64)])
+  map_d = torch.from_numpy(host).to(device)
+  n_map = abs_map.size
+  skip_d = torch.from_numpy(skipped.astype(np.uint8)).to(device) if skipped.any() else None
+  out_d = torch.empty(int(np.prod(out_shape)) * np_dtype.itemsize, dtype=torch.uint8,
+                      device=device)
+  ctx.bind_stream()
+  rc = _native.lib().sofima_warp_subvolume(
+      ctx.handle, img_d.data_ptr(), _SECTION_DTYPES[np_dtype],
+      (ctypes.c_int64 * 4)(*[int(v) for v in image.shape]), map_d.data_ptr(),
+      int(abs_map.dtype == np.float64), map_d.data_ptr() + 8 * n_map,
+      map_d.data_ptr() + 8 * (n_map + coord_map.shape[2]), int(coord_map.shape[2]),
+      int(coord_map.shape[3]), None if skip_d is None else skip_d.data_ptr(), code,
+      out_d.data_ptr(), out_shape[2], out_shape[3])
+  _native.check(ctx.handle, rc)
+  if is_tensor:
+    return out_d.view(img_d.dtype).reshape(out_shape)
+  warped = out_d.cpu().numpy().view(np_dtype).reshape(out_shape)
+  if labels_back is not None:
+    return labels_back[warped]
+  return warped.astype(orig_dtype)

@@ -1,0 +1,133 @@
+"""GPU parity tests of sofima_b200.warp.warp_subvolume through the C ABI:
+bit-exact against the outputs of the reference's warp.warp_subvolume (scipy + OpenCV,
+tests/golden/warp_cv_golden.npz) and against the oracle on seeded random cases."""
+
+import os
+
+import numpy as np
+import pytest
+import scipy.ndimage as ndi
+
+from oracle import warp_cv_oracle as wo
+from sofima_b200 import compat
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'warp_cv_golden.npz')
+
+
+@pytest.fixture(scope='module')
+def g():
+  return np.load(GOLDEN)
+
+
+@pytest.fixture(scope='module')
+def warp():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  from sofima_b200 import warp as w
+  return w
+
+
+def boxes(g):
+  b = g['a_boxes']
+  return tuple(compat.BoundingBox(start=b[i], size=b[i + 1]) for i in (0, 2, 4))
+
+
+@pytest.mark.parametrize('dt', ['u8', 'u16', 'f32'])
+@pytest.mark.parametrize('inter', ['nearest', 'linear', 'cubic', 'lanczos'])
+def test_reference_outputs(warp, g, dt, inter):
+  ib, mb, ob = boxes(g)
+  got = warp.warp_subvolume(g[f'a_image_{dt}'], ib, g['a_map'], mb, 8, ob, interpolation=inter)
+  want = g[f'a_{dt}_{inter}']
+  assert got.dtype == want.dtype and got.shape == want.shape
+  np.testing.assert_array_equal(got, want)
+
+
+def test_reference_variants(warp, g):
+  ib, mb, ob = boxes(g)
+  np.testing.assert_array_equal(
+      warp.warp_subvolume(g['a_image_u8'], ib, g['a_map'].astype(np.float32), mb, 8, ob),
+      g['a_u8_default_f32map'])
+  np.testing.assert_array_equal(
+      warp.warp_subvolume(g['a_image_u8'], ib, g['a_map'], mb, 8.0, ob, interpolation='linear',
+                          offset=0.5), g['a_u8_offset'])
+  got = warp.warp_subvolume(g['a_image_u16'].astype(np.uint32), ib, g['a_map'], mb, 8, ob,
+                            interpolation='linear')
+  assert got.dtype == np.uint32
+  np.testing.assert_array_equal(got, g['a_u32_linear'])
+  got = warp.warp_subvolume(g['b_seg'], ib, g['a_map'], mb, 8, ob)
+  assert got.dtype == np.uint64
+  np.testing.assert_array_equal(got, g['b_seg_warped'])
+  # the cv2 flag values are accepted like the names (INTER_LANCZOS4 = 4)
+  np.testing.assert_array_equal(
+      warp.warp_subvolume(g['a_image_u8'], ib, g['a_map'], mb, 8, ob, interpolation=4),
+      g['a_u8_lanczos'])
+
+
+def test_errors(warp, g):
+  ib, mb, ob = boxes(g)
+  with pytest.raises(ValueError):
+    warp.warp_subvolume(np.full((1, 3, 4, 4), 2**16, np.uint32), ib, g['a_map'], mb, 8, ob)
+  with pytest.raises(KeyError):
+    warp.warp_subvolume(g['a_image_u8'], ib, g['a_map'], mb, 8, ob, interpolation='spline')
+  with pytest.raises(NotImplementedError):
+    warp.warp_subvolume(g['a_image_u8'].astype(np.float64), ib, g['a_map'], mb, 8, ob)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_random_cases_against_oracle(warp, seed):
+  rng = np.random.default_rng(100 + seed)
+  n, nz = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+  h, w = int(rng.integers(60, 200)), int(rng.integers(60, 200))
+  stride = [4, 6.5, 10][seed]
+  my, mx = int(rng.integers(6, 20)), int(rng.integers(6, 20))
+  ib = compat.BoundingBox(start=rng.integers(0, 50, 3), size=(w, h, nz))
+  mb = compat.BoundingBox(start=(int(ib.start[0] // stride), int(ib.start[1] // stride),
+                                 ib.start[2]), size=(mx, my, nz))
+  ob = compat.BoundingBox(start=(ib.start[0] + int(rng.integers(-10, 10)),
+                                 ib.start[1] + int(rng.integers(-10, 10)), ib.start[2]),
+                          size=(int(rng.integers(40, 220)), int(rng.integers(40, 220)), nz))
+  cmap = np.stack([ndi.gaussian_filter(rng.standard_normal((nz, my, mx)), 1.5) * 30
+                   for _ in range(2)]).astype([np.float64, np.float32, np.float64][seed])
+  if seed == 1:
+    cmap[:, :, 2, 3] = np.nan
+  base = ndi.gaussian_filter(rng.random((n, nz, h, w)), (0, 0, 1, 1))
+  base = (base - base.min()) / (base.max() - base.min())
+  for img in ((base * 255).astype(np.uint8), (base * 65535).astype(np.uint16),
+              (base * 60000 - 30000).astype(np.int16), (base * 50 - 10).astype(np.float32)):
+    for inter in ('nearest', 'linear', 'cubic', 'lanczos'):
+      want = wo.warp_subvolume(img, ib, cmap, mb, stride, ob, interpolation=inter)
+      got = warp.warp_subvolume(img, ib, cmap, mb, stride, ob, interpolation=inter)
+      np.testing.assert_array_equal(got, want, err_msg=f'{img.dtype} {inter}')
+      assert want.any()
+
+
+def test_device_resident_section_stack(warp, g):
+  import torch
+  ib, mb, ob = boxes(g)
+  img = torch.from_numpy(g['a_image_u8']).cuda()
+  got = warp.warp_subvolume(img, ib, g['a_map'], mb, 8, ob, interpolation='lanczos')
+  assert got.is_cuda and got.dtype == torch.uint8
+  np.testing.assert_array_equal(got.cpu().numpy(), g['a_u8_lanczos'])
+
+
+def test_full_size_section_properties(warp):
+  """A 4096 x 4096 section: the identity map reproduces the image for every method, and an
+  integer translation reproduces the shifted image (zero outside)."""
+  rng = np.random.default_rng(7)
+  img = rng.integers(0, 256, (1, 1, 4096, 4096), dtype=np.uint8)
+  box = compat.BoundingBox(start=(0, 0, 0), size=(4096, 4096, 1))
+  mbox = compat.BoundingBox(start=(0, 0, 0), size=(129, 129, 1))
+  zero = np.zeros((2, 1, 129, 129))
+  for inter in ('nearest', 'linear', 'cubic', 'lanczos'):
+    np.testing.assert_array_equal(
+        warp.warp_subvolume(img, box, zero, mbox, 32, box, interpolation=inter), img)
+  shift = zero.copy()
+  shift[0] += 5
+  shift[1] -= 3
+  got = warp.warp_subvolume(img, box, shift, mbox, 32, box, interpolation='lanczos')
+  want = np.zeros_like(img)
+  want[0, 0, 3:, :-5] = img[0, 0, :-3, 5:]
+  np.testing.assert_array_equal(got, want)
