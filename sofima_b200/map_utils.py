@@ -1,6 +1,8 @@
 """Drop-in for the device-side part of `sofima.map_utils` (reference map_utils.py).
 
   compose_maps_fast        map_utils.py:616-734
+  to_absolute / to_relative  map_utils.py:150-224   (host bookkeeping on the small map array)
+  outer_box                map_utils.py:307-342   (host bookkeeping)
 
 Coordinate maps are in the reference's relative format `[2 or 3, z, y, x]`.  NumPy
 in -> NumPy out, CUDA torch tensors stay on the device.  The bilinear sampling
@@ -35,6 +37,58 @@ def _integral_starts(start, dim: int, name: str) -> list[int]:
     raise ValueError(f'{name} must be integral (got {vals.tolist()}): fractional map '
                      'origins are not supported by the CUDA backend')
   return [int(v) for v in vals]
+
+
+def _identity_offsets(shape, stride, box=None):
+  """Per-axis [z]yx absolute positions of the nodes of a map of `shape` (map_utils.py:128-147
+  plus the box shift of :169-177)."""
+  dim = len(shape)
+  stride = _as_vec(stride, dim)
+  grids = np.mgrid[tuple(slice(0, s) for s in shape)]
+  offs = [g * step for g, step in zip(grids, stride)]
+  if box is not None:
+    if not np.all(np.asarray(shape)[::-1] == np.asarray(box.size)[:dim]):
+      raise ValueError(f'box shape ({box.size}) mismatch with coord map ({shape})')
+    offs = [o + start * step for o, step, start in zip(offs, stride, box.start[:dim][::-1])]
+  return offs
+
+
+def to_absolute(coord_map: np.ndarray, stride, box=None) -> np.ndarray:
+  """Relative -> absolute coordinate map (map_utils.py:150-185): channel i (x, y[, z]) gets
+  the position of its node added; `box` places the map in the global frame."""
+  coord_map = np.array(coord_map)
+  dim = coord_map.shape[0]
+  offs = _identity_offsets(coord_map.shape[-dim:], stride, box)
+  for i in range(dim):
+    coord_map[i, ...] += offs[-(i + 1)]
+  return coord_map
+
+
+def to_relative(coord_map: np.ndarray, stride, box=None) -> np.ndarray:
+  """Absolute -> relative coordinate map (map_utils.py:190-224)."""
+  coord_map = np.array(coord_map)
+  dim = coord_map.shape[0]
+  offs = _identity_offsets(coord_map.shape[-dim:], stride, box)
+  for i in range(dim):
+    coord_map[i, ...] -= offs[-(i + 1)]
+  return coord_map
+
+
+def outer_box(coord_map: np.ndarray, box, stride, target_len=None):
+  """Box covering every target position the map refers to (map_utils.py:307-342), in units
+  of `target_len` (default: the map stride)."""
+  from . import compat  # pylint: disable=g-import-not-at-top
+  abs_map = to_absolute(coord_map, stride, box)
+  dim = coord_map.shape[0]
+  lens_xyz = _as_vec(target_len if target_len is not None else stride, dim)[::-1]
+  start = np.array(box.start).copy()
+  size = np.array(box.size).copy()
+  for i, tl in enumerate(lens_xyz):
+    lo, hi = np.nanmin(abs_map[i]), np.nanmax(abs_map[i])
+    lo = int(lo) // tl
+    start[i] = lo
+    size[i] = -(int(-hi) // tl) - lo + 1
+  return compat.BoundingBox(start=start, size=size)
 
 
 def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,

@@ -131,3 +131,38 @@ def test_full_size_section_properties(warp):
   want = np.zeros_like(img)
   want[0, 0, 3:, :-5] = img[0, 0, :-3, 5:]
   np.testing.assert_array_equal(got, want)
+
+
+def test_warp_by_map_processor(warp):
+  """processor.warp.WarpByMap (processor/warp.py:541-623) over in-memory volumes: every
+  section equals warp_subvolume on the boxes the processor derives; an integer shift map
+  renders the shifted data; 2x downsampling is the block mean of the full-resolution render."""
+  from sofima_b200.processor import warp as pwarp
+  rng = np.random.default_rng(5)
+  data = rng.integers(0, 256, (1, 3, 300, 320), dtype=np.uint8)
+  stride = 20
+  cmap = np.zeros((2, 3, 300 // stride + 1, 320 // stride + 1), np.float32)
+  cmap[0] += 6
+  cmap[1] -= 4
+  cmap[:, 1] = np.nan  # a section without a map stays empty
+  box = compat.BoundingBox(start=(40, 20, 0), size=(200, 160, 3))
+  proc = pwarp.WarpByMap(pwarp.WarpByMap.Config(stride=stride, map_volinfo=cmap,
+                                                data_volinfo=data, interpolation='lanczos'))
+  out = proc.process(compat.Subvolume(np.zeros((1, 3, 160, 200), np.uint8), box))[0]
+  assert out.bbox == box
+  want = np.zeros((1, 3, 160, 200), np.uint8)
+  want[:, ::2] = data[:, ::2, 20 - 4:180 - 4, 40 + 6:240 + 6]
+  np.testing.assert_array_equal(out.data, want)
+  # smooth map + downsampling
+  cmap2 = np.stack([ndi.gaussian_filter(rng.standard_normal(cmap.shape[1:]), (0, 2, 2)) * 20
+                    for _ in range(2)]).astype(np.float32)
+  full = pwarp.WarpByMap(pwarp.WarpByMap.Config(stride=stride, map_volinfo=cmap2,
+                                                data_volinfo=data, interpolation='linear'))
+  ref = full.process(compat.Subvolume(np.zeros((1, 3, 160, 200), np.uint8), box))[0].data
+  half = pwarp.WarpByMap(pwarp.WarpByMap.Config(stride=stride // 2, map_volinfo=cmap2,
+                                                data_volinfo=data, interpolation='linear',
+                                                downsample=2))
+  hbox = compat.BoundingBox(start=(20, 10, 0), size=(100, 80, 3))
+  got = half.process(compat.Subvolume(np.zeros((1, 3, 80, 100), np.uint8), hbox))[0].data
+  mean = ref.astype(np.int64).reshape(1, 3, 80, 2, 100, 2).sum(axis=(3, 5)) / 4.0
+  np.testing.assert_array_equal(got, mean.astype(np.uint8))
