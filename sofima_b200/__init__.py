@@ -16,5 +16,11 @@ def release_memory(keep_bytes: int = 0, device=None) -> None:
   scratch of the flow path; several GB after a large `flow_field` call) so that other
   users of the GPU -- torch's allocator, the mesh solver -- can have it.  Optional: the
   buffers are otherwise kept for the next call of the same geometry."""
+  import sys
   from . import _native
   _native.Context.get(device).trim(keep_bytes)
+  warp = sys.modules.get(__name__ + '.warp')
+  if warp is not None and not keep_bytes:
+    import torch
+    torch.cuda.synchronize()
+    warp._PINNED.clear()  # pinned section blocks of warp_subvolume

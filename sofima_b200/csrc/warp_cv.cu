@@ -125,23 +125,30 @@ struct Params {
   const void* image;     // [n][nz][ih][iw]
   void* out;             // [n][nz][oh][ow]
   const double* abs_map; // [2][nz][my][mx]: x then y source coordinate of every node
-  const double* gy;      // [my] node rows in output pixels
-  const double* gx;      // [mx]
+  const int* iy;         // [oh] interval of every output row in the node grid
+  const int* ix;         // [ow]
+  const double* ty;      // [oh] normalised distance within the interval
+  const double* tx;      // [ow]
   const uint8_t* skip;   // [nz] or null
   const Tables* tabs;
   int n, nz, ih, iw, oh, ow, my, mx;
   int map_f64;
 };
 
-__device__ __forceinline__ void interval(const double* __restrict__ g, int n, double q, int& i,
-                                         double& t) {
-  const double g0 = __ldg(g), g1 = __ldg(g + 1);
-  const double guess = floor((q - g0) / (g1 - g0));
-  i = guess < 0.0 ? 0 : (guess > (double)(n - 2) ? n - 2 : (int)guess);
-  while (i > 0 && q < __ldg(g + i)) --i;
-  while (i < n - 2 && q >= __ldg(g + i + 1)) ++i;
-  const double a = __ldg(g + i), b = __ldg(g + i + 1);
-  t = (q - a) / (b - a);
+// Interval and normalised distance of every output row / column in the node grid: they
+// depend on one axis only, so a small kernel tabulates them once per call and the per-pixel
+// kernel is free of float64 divisions.
+__global__ void axis_table_kernel(const double* __restrict__ g, int n, int count,
+                                  int* __restrict__ idx, double* __restrict__ dist) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const double g0 = g[0], g1 = g[1];
+  const double guess = floor(((double)q - g0) / (g1 - g0));
+  int i = guess < 0.0 ? 0 : (guess > (double)(n - 2) ? n - 2 : (int)guess);
+  while (i > 0 && (double)q < g[i]) --i;
+  while (i < n - 2 && (double)q >= g[i + 1]) ++i;
+  idx[q] = i;
+  dist[q] = ((double)q - g[i]) / (g[i + 1] - g[i]);
 }
 
 __device__ __forceinline__ double densify(const double* __restrict__ v, int mx, int iy, int ix,
@@ -182,6 +189,18 @@ template <> __device__ __forceinline__ int16_t saturate_out<int16_t>(float v) {
   return (int16_t)sat16(cv_round(v));
 }
 
+// acc + (two signed 16-bit weights) . (low / high two unsigned bytes of `px`)
+__device__ __forceinline__ int dp2a_lo(int w, uint32_t px, int acc) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi(int w, uint32_t px, int acc) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
+  return d;
+}
+
 // Integer-table sampling of a uint8 section.
 template <int K>
 __device__ __forceinline__ uint8_t sample_u8(const uint8_t* __restrict__ img, int ih, int iw,
@@ -204,7 +223,24 @@ __device__ __forceinline__ uint8_t sample_u8(const uint8_t* __restrict__ img, in
   } else {
     const int16_t* w = K == 4 ? tabs->itab4[fy * kTab + fx] : tabs->itab8[fy * kTab + fx];
     const bool inner = x0 >= 0 && x0 + K <= iw && y0 >= 0 && y0 + K <= ih;
-    if (inner) {
+    if (inner && K == 8) {
+      // Footprint inside the section: every row is 8 consecutive bytes, fetched as the (2 or
+      // 3) aligned words around them; the 16-bit weights are consumed pairwise by dp2a.
+      const uint8_t* s = img + (size_t)y0 * iw + x0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s + (size_t)i * iw);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = sh ? __ldg(wp + 2) : 0u;
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        const int4 q = __ldg(reinterpret_cast<const int4*>(w + i * 8));
+        acc = dp2a_lo(q.x, lo, acc);
+        acc = dp2a_hi(q.y, lo, acc);
+        acc = dp2a_lo(q.z, hi, acc);
+        acc = dp2a_hi(q.w, hi, acc);
+      }
+    } else if (inner) {
       const uint8_t* s = img + (size_t)y0 * iw + x0;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
@@ -296,10 +332,8 @@ __global__ void __launch_bounds__(kBX* kBY) remap_kernel(const Params p) {
   const int z = blockIdx.z;
   if (x >= p.ow || y >= p.oh) return;
   if (p.skip && p.skip[z]) return;  // the output is zero-filled beforehand
-  int iy, ix;
-  double ty, tx;
-  interval(p.gy, p.my, (double)y, iy, ty);
-  interval(p.gx, p.mx, (double)x, ix, tx);
+  const int iy = __ldg(p.iy + y), ix = __ldg(p.ix + x);
+  const double ty = __ldg(p.ty + y), tx = __ldg(p.tx + x);
   const size_t plane = (size_t)p.my * p.mx;
   const float cx = (float)densify(p.abs_map + (size_t)z * plane, p.mx, iy, ix, ty, tx, p.map_f64);
   const float cy = (float)densify(p.abs_map + ((size_t)p.nz + z) * plane, p.mx, iy, ix, ty, tx,
@@ -384,7 +418,13 @@ extern "C" int sofima_warp_subvolume(sofima_ctx* ctx, const void* image, int img
     }
   }
   warpcv::Params p;
-  p.image = image; p.out = out; p.abs_map = abs_map; p.gy = grid_y; p.gx = grid_x;
+  p.image = image; p.out = out; p.abs_map = abs_map;
+  void* axes = nullptr;
+  const size_t n_ax = (size_t)oh + (size_t)ow;
+  if (int rc = scratch(ctx, "warpcv.axes", n_ax * (sizeof(double) + sizeof(int)), &axes)) return rc;
+  double* dist = static_cast<double*>(axes);
+  int* idx = reinterpret_cast<int*>(dist + n_ax);
+  p.ty = dist; p.tx = dist + oh; p.iy = idx; p.ix = idx + oh;
   p.skip = skip; p.tabs = static_cast<const warpcv::Tables*>(dtabs);
   p.n = (int)n; p.nz = (int)nz; p.ih = (int)ih; p.iw = (int)iw; p.oh = (int)oh; p.ow = (int)ow;
   p.my = (int)my; p.mx = (int)mx; p.map_f64 = map_is_f64;
@@ -393,6 +433,10 @@ extern "C" int sofima_warp_subvolume(sofima_ctx* ctx, const void* image, int img
     const cudaError_t e = cudaMemsetAsync(out, 0, (size_t)(n * nz * oh * ow) * esize, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, SOFIMA_ECUDA, "memset: %s", cudaGetErrorString(e));
   }
+  warpcv::axis_table_kernel<<<(unsigned)ceil_div<int64_t>(oh, 256), 256, 0, ctx->stream>>>(
+      grid_y, (int)my, (int)oh, idx, dist);
+  warpcv::axis_table_kernel<<<(unsigned)ceil_div<int64_t>(ow, 256), 256, 0, ctx->stream>>>(
+      grid_x, (int)mx, (int)ow, idx + oh, dist + oh);
   static const int ks[4] = {1, 2, 4, 8};
   const int k = ks[interpolation];
   switch (img_dtype) {

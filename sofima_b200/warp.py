@@ -237,29 +237,95 @@ def warp_subvolume(image, image_box, coord_map, map_box, stride, out_box, interp
   dev = image.device.index if is_tensor and image.is_cuda else None
   ctx = _native.Context.get(dev)
   device = torch.device('cuda', ctx.device)
+  is_f64 = int(abs_map.dtype == np.float64)
+  grids = [np.asarray(grid_y, np.float64), np.asarray(grid_x, np.float64)]
+  my, mx = int(coord_map.shape[2]), int(coord_map.shape[3])
+
+  def launch(img_d, z0, z1, out_d):
+    """Sections [z0, z1) of a device-resident [n, z1 - z0, y, x] block -> out_d."""
+    nzc = z1 - z0
+    host = np.concatenate([np.ascontiguousarray(abs_map[:, z0:z1], dtype=np.float64).ravel()]
+                          + grids)
+    map_d = torch.from_numpy(host).to(device, non_blocking=True)
+    n_map = 2 * nzc * my * mx
+    skip_d = None
+    if skipped[z0:z1].any():
+      skip_d = torch.from_numpy(skipped[z0:z1].astype(np.uint8)).to(device)
+    ctx.bind_stream()
+    rc = _native.lib().sofima_warp_subvolume(
+        ctx.handle, img_d.data_ptr(), _SECTION_DTYPES[np_dtype],
+        (ctypes.c_int64 * 4)(int(image.shape[0]), nzc, int(image.shape[2]),
+                             int(image.shape[3])),
+        map_d.data_ptr(), is_f64, map_d.data_ptr() + 8 * n_map,
+        map_d.data_ptr() + 8 * (n_map + my), my, mx,
+        None if skip_d is None else skip_d.data_ptr(), code, out_d.data_ptr(), out_shape[2],
+        out_shape[3])
+    _native.check(ctx.handle, rc)
+    return map_d, skip_d  # referenced until the stream has consumed them
+
   if is_tensor:
     img_d = image.to(device).contiguous()
-  else:
-    img_d = torch.from_numpy(np.ascontiguousarray(image).view(np.uint8)).to(device)
-  host = np.concatenate([np.ascontiguousarray(abs_map, dtype=np.float64).ravel(),
-                         np.asarray(grid_y, np.float64), np.asarray(grid_x, np.float64)])
-  map_d = torch.from_numpy(host).to(device)
-  n_map = abs_map.size
-  skip_d = torch.from_numpy(skipped.astype(np.uint8)).to(device) if skipped.any() else None
-  out_d = torch.empty(int(np.prod(out_shape)) * np_dtype.itemsize, dtype=torch.uint8,
-                      device=device)
-  ctx.bind_stream()
-  rc = _native.lib().sofima_warp_subvolume(
-      ctx.handle, img_d.data_ptr(), _SECTION_DTYPES[np_dtype],
-      (ctypes.c_int64 * 4)(*[int(v) for v in image.shape]), map_d.data_ptr(),
-      int(abs_map.dtype == np.float64), map_d.data_ptr() + 8 * n_map,
-      map_d.data_ptr() + 8 * (n_map + coord_map.shape[2]), int(coord_map.shape[2]),
-      int(coord_map.shape[3]), None if skip_d is None else skip_d.data_ptr(), code,
-      out_d.data_ptr(), out_shape[2], out_shape[3])
-  _native.check(ctx.handle, rc)
-  if is_tensor:
+    out_d = torch.empty(int(np.prod(out_shape)) * np_dtype.itemsize, dtype=torch.uint8,
+                        device=device)
+    launch(img_d, 0, out_shape[1], out_d)
     return out_d.view(img_d.dtype).reshape(out_shape)
-  warped = out_d.cpu().numpy().view(np_dtype).reshape(out_shape)
+
+  # Host arrays: blocks of sections travel through two pairs of pinned buffers, so that the
+  # host copies of one block overlap the transfers and the kernel of the previous one.
+  n, nz = out_shape[0], out_shape[1]
+  warped = np.empty(out_shape, np_dtype)
+  in_sec = n * image.shape[2] * image.shape[3] * np_dtype.itemsize
+  out_sec = n * out_shape[2] * out_shape[3] * np_dtype.itemsize
+  zc = max(1, min(nz, _BLOCK_BYTES // max(in_sec, out_sec, 1)))
+  pins = _pinned_blocks(zc * in_sec, zc * out_sec)
+  pending = None  # (z0, z1, pinned out view, event, keep-alive)
+  for k, z0 in enumerate(range(0, nz, zc)):
+    z1 = min(nz, z0 + zc)
+    pin_in, pin_out, done = pins[k % 2]
+    if done[0] is not None:
+      done[0].synchronize()  # the block that used this pair two rounds ago has left it
+    src = pin_in[:(z1 - z0) * in_sec].view(torch.uint8)
+    np.copyto(src.numpy().view(np_dtype).reshape((n, z1 - z0) + tuple(image.shape[2:])),
+              image[:, z0:z1])
+    img_d = src.to(device, non_blocking=True)
+    out_d = torch.empty((z1 - z0) * out_sec, dtype=torch.uint8, device=device)
+    keep = launch(img_d, z0, z1, out_d)
+    dst = pin_out[:(z1 - z0) * out_sec]
+    dst.copy_(out_d, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    done[0] = ev
+    if pending is not None:
+      _collect(warped, pending, np_dtype)
+    pending = (z0, z1, dst, ev, (img_d, out_d, keep))
+  if pending is not None:
+    _collect(warped, pending, np_dtype)
   if labels_back is not None:
     return labels_back[warped]
-  return warped.astype(orig_dtype)
+  return warped.astype(orig_dtype, copy=False)
+
+
+_BLOCK_BYTES = 48 << 20
+_PINNED: dict = {}
+
+
+def _pinned_blocks(in_bytes: int, out_bytes: int):
+  """Two (pinned in, pinned out, [event]) triples per thread, grown on demand."""
+  import threading
+  torch = _mesh._torch()
+  key = threading.get_ident()
+  cur = _PINNED.get(key)
+  if cur is None or cur[0][0].numel() < in_bytes or cur[0][1].numel() < out_bytes:
+    cur = [(torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True),
+            torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True), [None])
+           for _ in range(2)]
+    _PINNED[key] = cur
+  return cur
+
+
+def _collect(warped: np.ndarray, pending, np_dtype):
+  z0, z1, dst, ev, _ = pending
+  ev.synchronize()
+  n = warped.shape[0]
+  np.copyto(warped[:, z0:z1],
+            dst.numpy().view(np_dtype).reshape((n, z1 - z0) + warped.shape[2:]))
