@@ -2,7 +2,16 @@
 
   compose_maps_fast        map_utils.py:616-734
   to_absolute / to_relative  map_utils.py:150-224   (host bookkeeping on the small map array)
-  outer_box                map_utils.py:307-342   (host bookkeeping)
+  outer_box / inner_box    map_utils.py:307-389   (host bookkeeping)
+  fill_missing             map_utils.py:227-304   (host, SciPy qhull like the reference)
+  invert_map               map_utils.py:392-487   (host, SciPy qhull like the reference)
+  resample_map             map_utils.py:490-546   (host, SciPy qhull like the reference)
+
+The scattered-data steps (Delaunay triangulation + piecewise-linear / nearest lookup) work
+on the coarse map nodes -- thousands of points, not pixels -- and are scipy.spatial /
+scipy.interpolate calls in the reference; they stay SciPy calls here, so the values are the
+reference's.  The per-pixel work that follows them (warp.warp_subvolume, ndimage_warp) is
+what runs on the GPU.
 
 Coordinate maps are in the reference's relative format `[2 or 3, z, y, x]`.  NumPy
 in -> NumPy out, CUDA torch tensors stay on the device.  The bilinear sampling
@@ -17,6 +26,8 @@ import ctypes
 from typing import Sequence
 
 import numpy as np
+from scipy import interpolate as _interpolate
+from scipy import spatial as _spatial
 
 from . import _native
 from . import mesh as _mesh
@@ -89,6 +100,178 @@ def outer_box(coord_map: np.ndarray, box, stride, target_len=None):
     start[i] = lo
     size[i] = -(int(-hi) // tl) - lo + 1
   return compat.BoundingBox(start=start, size=size)
+
+
+def _interpolate_points(data_points, query_points, *values, method: str = 'linear'):
+  """Scattered-data interpolation of several fields at once (map_utils.py:70-117):
+  `data_points` / `query_points` are per-axis coordinate arrays (x, y[, z]); returns
+  [len(values), n_query].  Outside the convex hull linear / cubic give NaN."""
+  if len(data_points) != len(query_points):
+    raise ValueError('Data and query points dimensionalities needs to match, are: '
+                     f'{len(data_points)} and {len(query_points)}')
+  if method == 'nearest':
+    lookup = _interpolate.NearestNDInterpolator(data_points, values[0])
+    fields = [lookup(query_points)]
+    for val in values[1:]:
+      lookup.values = val
+      fields.append(lookup(query_points))
+    return np.array(fields)
+  if method not in ('linear', 'cubic'):
+    raise ValueError(f'unknown interpolation method {method!r}')
+  pts = np.ascontiguousarray(np.array(data_points).T, dtype=np.double)
+  tri = _spatial.Delaunay(pts)
+  stacked = np.array(values).T  # [n_points, n_fields]
+  if method == 'linear':
+    lookup = _interpolate.LinearNDInterpolator(tri, stacked, fill_value=np.nan)
+  else:
+    lookup = _interpolate.CloughTocher2DInterpolator(tri, stacked, fill_value=np.nan)
+  return lookup(query_points).T
+
+
+_QhullError = getattr(_spatial, 'QhullError', None) or _spatial.qhull.QhullError
+
+
+def fill_missing(coord_map: np.ndarray, *, extrapolate=False, invalid_to_zero=False,
+                 interpolate_first=True) -> np.ndarray:
+  """Replaces non-finite nodes of a relative map (map_utils.py:227-304): linear
+  interpolation inside the hull of the valid nodes, then (optionally) nearest-neighbour
+  extrapolation; 2-d maps are processed section by section."""
+  if not np.any(np.isnan(coord_map)):
+    return coord_map
+  dim = coord_map.shape[0]
+  grid = np.mgrid[tuple(slice(0, n) for n in coord_map.shape[-dim:])]  # [z]yx
+  axes_xyz = grid[::-1]
+  queries = tuple(a.ravel() for a in axes_xyz)
+  node_shape = coord_map.shape[-dim:]
+
+  def fill(section):
+    out = section.copy()
+    valid = np.all(np.isfinite(section), axis=0)
+    if not np.any(valid) and invalid_to_zero:
+      out[...] = 0
+      return out
+    if interpolate_first:
+      try:
+        fields = _interpolate_points(tuple(a[valid] for a in axes_xyz), queries,
+                                     *[c[valid] for c in section])
+        for i, f in enumerate(fields):
+          out[i, ...] = f.reshape(node_shape)
+      except _QhullError:
+        pass
+    if extrapolate:
+      valid = np.all(np.isfinite(out), axis=0)
+      if not np.all(valid):
+        fields = _interpolate_points(tuple(a[valid] for a in axes_xyz), queries,
+                                     *[c[valid] for c in out], method='nearest')
+        for i, f in enumerate(fields):
+          out[i, ...] = f.reshape(node_shape)
+    return out
+
+  if dim == 2:
+    return np.stack([fill(coord_map[:, z, ...]) for z in range(coord_map.shape[1])], axis=1)
+  return fill(coord_map)
+
+
+def inner_box(coord_map: np.ndarray, box, stride):
+  """Box all of whose nodes are reached by the map (map_utils.py:345-389)."""
+  from . import compat  # pylint: disable=g-import-not-at-top
+  dim = coord_map.shape[0]
+  assert dim in (2, 3)
+  stride = _as_vec(stride, dim)
+  full = to_absolute(fill_missing(coord_map, extrapolate=True), stride, box)
+  lo, hi = [], []
+  for i in range(dim):  # x, y[, z]; component i varies along array axis -(i + 1)
+    axis = -(i + 1)
+    step = stride[axis]
+    a = np.max(np.min(full[i, ...], axis=axis))
+    b = np.min(np.max(full[i, ...], axis=axis))
+    lo.append(int(-(-a // step)))
+    hi.append(b // step)
+  if dim == 2:
+    return compat.BoundingBox(start=(lo[0], lo[1], box.start[2]),
+                              size=(hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, box.size[2]))
+  return compat.BoundingBox(start=lo, size=[h - l + 1 for l, h in zip(lo, hi)])
+
+
+def invert_map(coord_map: np.ndarray, src_box, dst_box, stride) -> np.ndarray:
+  """(x, y[, z]) -> (u, v[, w]) map inverted on the nodes of `dst_box`
+  (map_utils.py:392-487): the valid source nodes are scattered at their targets and the
+  source positions are interpolated linearly at the regular destination nodes."""
+  coord_map = coord_map.astype(np.float64)
+  dim = coord_map.shape[0]
+  if dim not in (2, 3):
+    raise NotImplementedError()
+  stride = _as_vec(stride, dim)
+  # frame with its origin at the first destination node
+  src_box = src_box.adjusted_by(start=-dst_box.start, end=-dst_box.start)
+  dst_box = dst_box.adjusted_by(start=-dst_box.start, end=-dst_box.start)
+  coord_map = to_absolute(coord_map, stride, src_box)
+
+  def node_positions(box):  # [z]yx arrays of node positions in pixels
+    grid = np.mgrid[tuple(slice(0, int(n)) for n in box.size[:dim][::-1])]
+    for i in range(dim):
+      grid[i] = (grid[i] + box.start[dim - i - 1]) * stride[i]
+    return grid
+
+  src_pos = node_positions(src_box)
+  dst_pos = node_positions(dst_box)
+  queries = tuple(q.ravel() for q in dst_pos[::-1])  # uv[w]
+  if dim == 2:
+    out = np.full((2, coord_map.shape[1], dst_box.size[1], dst_box.size[0]), np.nan,
+                  dtype=coord_map.dtype)
+    for z in range(coord_map.shape[1]):
+      valid = np.all(np.isfinite(coord_map[:, z, ...]), axis=0)
+      if not np.any(valid):
+        continue
+      try:
+        u, v = _interpolate_points(tuple(c[z][valid] for c in coord_map), queries,
+                                   *[p[valid] for p in src_pos[::-1]])
+      except _QhullError:
+        continue
+      out[0, z, ...] = u.reshape(dst_pos[1].shape)
+      out[1, z, ...] = v.reshape(dst_pos[0].shape)
+    return to_relative(out, stride, dst_box)
+  out = np.full((3, dst_box.size[2], dst_box.size[1], dst_box.size[0]), np.nan,
+                dtype=coord_map.dtype)
+  valid = np.all(np.isfinite(coord_map), axis=0)
+  if not np.any(valid):
+    return out
+  try:
+    fields = _interpolate_points(tuple(c[valid] for c in coord_map), queries,
+                                 *[p[valid] for p in src_pos[::-1]])
+    for i, f in enumerate(fields):
+      out[i, ...] = f.reshape(dst_pos[0].shape)
+  except _QhullError:
+    pass
+  return to_relative(out, stride, dst_box)
+
+
+def resample_map(coord_map: np.ndarray, src_box, dst_box, src_stride: float,
+                 dst_stride: float, method='linear') -> np.ndarray:
+  """Relative [2, z, y, x] map resampled on a grid of another spacing
+  (map_utils.py:490-546)."""
+  assert coord_map.shape[0] == 2
+  sy, sx = np.mgrid[:src_box.size[1], :src_box.size[0]]
+  sy = (sy + src_box.start[1]) * src_stride
+  sx = (sx + src_box.start[0]) * src_stride
+  ty, tx = np.mgrid[:dst_box.size[1], :dst_box.size[0]]
+  ty = (ty + dst_box.start[1]) * dst_stride
+  tx = (tx + dst_box.start[0]) * dst_stride
+  out = np.full((2, coord_map.shape[1], dst_box.size[1], dst_box.size[0]), np.nan,
+                dtype=coord_map.dtype)
+  for z in range(coord_map.shape[1]):
+    valid = np.isfinite(coord_map[0, z, ...])
+    if not np.any(valid):
+      continue
+    try:
+      u, v = _interpolate_points((sx[valid], sy[valid]), (tx.ravel(), ty.ravel()),
+                                 coord_map[0, z, ...][valid], coord_map[1, z, ...][valid],
+                                 method=method)
+    except _QhullError:
+      continue
+    out[0, z, ...] = u.reshape(tx.shape)
+    out[1, z, ...] = v.reshape(ty.shape)
+  return out
 
 
 def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,

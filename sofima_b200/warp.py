@@ -329,3 +329,95 @@ def _collect(warped: np.ndarray, pending, np_dtype):
   n = warped.shape[0]
   np.copyto(warped[:, z0:z1],
             dst.numpy().view(np_dtype).reshape((n, z1 - z0) + warped.shape[2:]))
+
+
+def render_tiles(tiles, coord_maps, stride=(20, 20), margin: int = 50, parallelism: int = 1,
+                 width=None, height=None, use_clahe: bool = False, clahe_kwargs=None,
+                 margin_overrides=None, return_warped_tiles: bool = False, tile_masks=None):
+  """Warps a grid of tiles into one canvas (warp.py:338-535).
+
+  Args:
+    tiles: (x, y) tile coordinate -> [y, x] image; all tiles have the same shape
+    coord_maps: (x, y) -> [2, 1, my, mx] forward coordinate map of the tile
+    stride: map stride in pixels (equal in x and y)
+    margin: pixels at the tile edges that are not rendered
+    parallelism: accepted for compatibility (host threads in the reference; the tiles
+      are warped one after the other on the GPU)
+    width, height: canvas size; inferred from the tile grid when missing
+    use_clahe, clahe_kwargs: CLAHE (skimage.exposure.equalize_adapthist) before warping
+    margin_overrides: (x, y) -> (top, bottom, left, right) margins
+    return_warped_tiles: also return {(x, y): (x0, y0, warped tile)}
+    tile_masks: (x, y) -> array like the tile; only non-zero pixels are rendered
+
+  Returns:
+    (canvas [height, width], bool array of the pixels covered by tile content)
+    [+ the dict of warped tiles].
+  The map inversion runs on the map nodes with SciPy exactly as in the reference
+  (map_utils.invert_map / fill_missing); the per-pixel warp is `warp_subvolume` on the GPU.
+  """
+  del parallelism
+  from . import map_utils  # pylint: disable=g-import-not-at-top
+  if stride[0] != stride[1]:
+    raise NotImplementedError('Currently only equal strides in XY are supported.')
+  first = next(iter(tiles.values()))
+  ty, tx = first.shape
+  image_box = compat.BoundingBox(start=(0, 0, 0), size=(tx, ty, 1))
+  my, mx = next(iter(coord_maps.values())).shape[-2:]
+  map_box = compat.BoundingBox(start=(0, 0, 0), size=(mx, my, 1))
+  if width is None or height is None:
+    height = ty * (max(y for _, y in tiles) + 1)
+    width = tx * (max(x for x, _ in tiles) + 1)
+  canvas = np.zeros((height, width), dtype=first.dtype)
+  covered = np.zeros((height, width), dtype=bool)
+  warped_tiles = {}
+  clahe_kwargs = clahe_kwargs or {}
+
+  for (tile_x, tile_y), coord_map in coord_maps.items():
+    img = tiles.get((tile_x, tile_y))
+    if img is None:
+      continue
+    # inverse map on a node box covering everything the tile maps to (+1 node of context)
+    tg_box = map_utils.outer_box(coord_map, map_box, stride[0])
+    tg_box = tg_box.adjusted_by(start=(-1, -1, 0), end=(1, 1, 0))
+    inverse = map_utils.invert_map(coord_map, map_box, tg_box, stride[0])
+    inverse = map_utils.fill_missing(inverse, extrapolate=True)
+    # 1 inside the margins (and the tile mask), warped together with the image
+    keep = np.zeros_like(img)
+    if margin_overrides is not None and (tile_x, tile_y) in margin_overrides:
+      top, bottom, left, right = margin_overrides[tile_x, tile_y]
+      keep[top:-(bottom + 1), left:-(right + 1)] = 1
+    else:
+      keep[margin:-(margin + 1), margin:-(margin + 1)] = 1
+    if use_clahe:
+      try:
+        import skimage.exposure  # pylint: disable=g-import-not-at-top
+      except ImportError as e:
+        raise NotImplementedError('use_clahe needs scikit-image') from e
+      img = (skimage.exposure.equalize_adapthist(img, **clahe_kwargs)
+             * np.iinfo(img.dtype).max).astype(img.dtype)
+    if tile_masks is not None and tile_masks.get((tile_x, tile_y)) is not None:
+      keep[tile_masks[tile_x, tile_y] == 0] = 0
+    out_box = compat.BoundingBox(
+        start=((tg_box.start[0] + 1) * stride[1], (tg_box.start[1] + 1) * stride[0], 0),
+        size=(tg_box.size[0] * stride[1], tg_box.size[1] * stride[0], 1))
+    w_img, w_keep = warp_subvolume(np.stack([img, keep])[:, None], image_box, inverse, tg_box,
+                                   stride[0], out_box=out_box)
+    w_img, w_keep = w_img[0], w_keep[0].astype(bool)
+    # canvas position relative to the nominal tile position; trim what sticks out
+    y0 = ty * tile_y + int(out_box.start[1])
+    x0 = tx * tile_x + int(out_box.start[0])
+    if x0 < 0:
+      w_img, w_keep, x0 = w_img[:, -x0:], w_keep[:, -x0:], 0
+    if y0 < 0:
+      w_img, w_keep, y0 = w_img[-y0:], w_keep[-y0:], 0
+    dst = canvas[y0:y0 + w_img.shape[0], x0:x0 + w_img.shape[1]]
+    w_img = w_img[:dst.shape[0], :dst.shape[1]]
+    w_keep = w_keep[:dst.shape[0], :dst.shape[1]]
+    if return_warped_tiles:
+      warped_tiles[tile_x, tile_y] = x0, y0, w_img
+    covered[y0:y0 + w_img.shape[0], x0:x0 + w_img.shape[1]][w_keep] = True
+    w_keep = w_keep & (w_img > 0)  # never paint unrendered (zero) pixels
+    dst[w_keep] = w_img[w_keep]
+  if return_warped_tiles:
+    return canvas, covered, warped_tiles
+  return canvas, covered

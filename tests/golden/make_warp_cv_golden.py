@@ -97,6 +97,35 @@ def main():
   seg = np.kron(seg, np.ones((1, 1, 10, 10), np.uint64))[:, :, :h, :w]
   out['b_seg'] = seg
   out['b_seg_warped'] = warp.warp_subvolume(seg, image_box, cmap, map_box, 8, out_box)
+  # Case C: render_tiles on a 2 x 2 grid of 160 x 200 tiles (stride 20), smooth forward maps,
+  # one NaN node, one tile mask, margin overrides; canvas inferred.
+  th, tw, st = 160, 200, 20
+  big = ndi.gaussian_filter(rng.random((2 * th + 60, 2 * tw + 60)), 1.5)
+  big = ((big - big.min()) / (big.max() - big.min()) * 254 + 1).astype(np.uint8)
+  tiles, maps = {}, {}
+  for ty_ in range(2):
+    for tx_ in range(2):
+      tiles[tx_, ty_] = np.ascontiguousarray(
+          big[30 + ty_ * (th - 20):30 + ty_ * (th - 20) + th,
+              30 + tx_ * (tw - 20):30 + tx_ * (tw - 20) + tw])
+      m = np.stack([smooth((1, th // st, tw // st), 2, 12), smooth((1, th // st, tw // st), 2, 12)])
+      m[0] -= 10 * tx_
+      m[1] -= 10 * ty_
+      maps[tx_, ty_] = m
+  maps[1, 0][:, 0, 3, 4] = np.nan
+  mask = np.ones((th, tw), np.uint8)
+  mask[40:70, 50:90] = 0
+  for (tx_, ty_), t in tiles.items():
+    out[f'c_tile_{tx_}{ty_}'] = t
+    out[f'c_map_{tx_}{ty_}'] = maps[tx_, ty_]
+  out['c_mask_01'] = mask
+  canvas, cov, wt = warp.render_tiles(tiles, maps, stride=(st, st), margin=10,
+                                      return_warped_tiles=True, tile_masks={(0, 1): mask},
+                                      margin_overrides={(1, 1): (5, 8, 12, 3)})
+  out['c_canvas'], out['c_covered'] = canvas, cov
+  for (tx_, ty_), (x0, y0, w) in wt.items():
+    out[f'c_warped_{tx_}{ty_}'] = w
+    out[f'c_pos_{tx_}{ty_}'] = np.array([x0, y0])
   path = os.path.join(HERE, 'warp_cv_golden.npz')
   np.savez_compressed(path, **out)
   print('warp_cv_golden.npz', os.path.getsize(path) // 1024, 'KiB')

@@ -38,3 +38,82 @@ def test_outer_box():
   coord_map[1, 0, 0, 1] = -2
   assert map_utils.outer_box(coord_map, box, stride=5) == compat.BoundingBox(
       start=(99, 199, 10), size=(53, 52, 1))
+
+
+def test_fill_missing():
+  hy, hx = np.mgrid[:50, :50]
+  coord_map = np.zeros([2, 1, 50, 50])
+  coord_map[0, 0, ...] = np.sin(hx / 25)
+  coord_map[1, 0, ...] = np.cos(hy / 25)
+  with_gap = coord_map.copy()
+  with_gap[:, 0, 24:28, 38:42] = np.nan
+  np.testing.assert_array_almost_equal(map_utils.fill_missing(with_gap), coord_map, decimal=2)
+  with_gap = coord_map.copy()
+  with_gap[:, 0, -1, :] = np.nan
+  assert np.all(np.isnan(map_utils.fill_missing(with_gap)[:, 0, -1, :]))
+  filled = map_utils.fill_missing(with_gap, extrapolate=True)
+  np.testing.assert_array_almost_equal(filled[1, 0, -1, :], coord_map[1, 0, -1, :], decimal=1)
+  with_gap[...] = np.nan
+  assert np.all(map_utils.fill_missing(with_gap, invalid_to_zero=True) == 0)
+  assert map_utils.fill_missing(coord_map) is coord_map  # nothing to do: same object
+
+
+def test_inner_box():
+  box = compat.BoundingBox(start=(100, 200, 10), size=(50, 50, 1))
+  coord_map = np.zeros([2, 1, 50, 50])
+  coord_map[1, :, ...] = -30
+  coord_map[1, :, 0, :] = -40
+  coord_map[1, :, -1, :] = -25
+  assert map_utils.inner_box(coord_map, box, stride=10) == compat.BoundingBox(
+      start=(100, 196, 10), size=(50, 51, 1))
+  coord_map = np.zeros([2, 1, 50, 50])
+  coord_map[0, :, :, 0] = -9
+  coord_map[0, :, :, -1] = 9
+  assert map_utils.inner_box(coord_map, box, stride=10) == compat.BoundingBox(
+      start=(100, 200, 10), size=(50, 50, 1))
+
+
+def test_inner_box3d():
+  box = compat.BoundingBox(start=(100, 200, 200), size=(50, 50, 50))
+  coord_map = np.zeros([3, 50, 50, 50])
+  coord_map[2, ...] = -30
+  coord_map[2, 0, :, :] = -40
+  coord_map[2, -1, :, :] = -25
+  assert map_utils.inner_box(coord_map, box, stride=10) == compat.BoundingBox(
+      start=(100, 200, 196), size=(50, 50, 51))
+
+
+def test_invert_map():
+  box = compat.BoundingBox(start=(100, 200, 10), size=(50, 50, 1))
+  _, hx = np.mgrid[:50, :50]
+  coord_map = np.zeros([2, 1, 50, 50])
+  coord_map[1, 0, ...] = np.sin(hx / 25) * 20
+  inv_map = map_utils.invert_map(coord_map, box, box, 40.0)
+  np.testing.assert_array_almost_equal(inv_map[:, :, 1:, 1:], -coord_map[:, :, 1:, 1:],
+                                       decimal=5)
+
+
+def test_invert_map_3d():
+  box = compat.BoundingBox(start=(100, 200, 10), size=(20, 20, 5))
+  _, _, hx = np.mgrid[:5, :20, :20]
+  coord_map = np.zeros([3, 5, 20, 20])
+  coord_map[1, ...] = np.sin(hx / 25) * 20
+  inv_map = map_utils.invert_map(coord_map, box, box, 40.0)
+  np.testing.assert_array_almost_equal(inv_map[:, 1:, 1:, 1:], -coord_map[:, 1:, 1:, 1:],
+                                       decimal=5)
+
+
+def test_resample_map():
+  box = compat.BoundingBox(start=(100, 200, 10), size=(50, 50, 1))
+  hy, hx = np.mgrid[:50, :50]
+  coord_map = np.zeros([2, 1, 50, 50])
+  coord_map[0, 0, ...] = np.sin(hx / 25) * 20
+  coord_map[1, 0, ...] = np.cos(hy / 25) * 20
+  hy, hx = np.mgrid[:100, :100]
+  expected = np.zeros([2, 1, 100, 100])
+  expected[0, 0, ...] = np.sin(hx / 50) * 20
+  expected[1, 0, ...] = np.cos(hy / 50) * 20
+  dst_box = compat.BoundingBox(start=(102, 203, 10), size=(48, 47, 1)).scale([2, 2, 1.0])
+  resampled = map_utils.resample_map(coord_map, box, dst_box, 40, 20)
+  np.testing.assert_array_almost_equal(resampled[:, :, :-1, :-1], expected[:, :, 6:-1, 4:-1],
+                                       decimal=2)

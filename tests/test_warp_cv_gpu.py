@@ -166,3 +166,24 @@ def test_warp_by_map_processor(warp):
   got = half.process(compat.Subvolume(np.zeros((1, 3, 80, 100), np.uint8), hbox))[0].data
   mean = ref.astype(np.int64).reshape(1, 3, 80, 2, 100, 2).sum(axis=(3, 5)) / 4.0
   np.testing.assert_array_equal(got, mean.astype(np.uint8))
+
+
+def test_render_tiles_reference_outputs(warp, g):
+  """warp.render_tiles (warp.py:338-535) on a 2 x 2 tile grid: canvas, coverage mask and the
+  per-tile renders equal the reference's (scipy map inversion + OpenCV Lanczos remap)."""
+  keys = [(0, 0), (0, 1), (1, 0), (1, 1)]
+  tiles = {k: g[f'c_tile_{k[0]}{k[1]}'] for k in keys}
+  maps = {k: g[f'c_map_{k[0]}{k[1]}'] for k in keys}
+  canvas, covered, wt = warp.render_tiles(
+      tiles, maps, stride=(20, 20), margin=10, return_warped_tiles=True,
+      tile_masks={(0, 1): g['c_mask_01']}, margin_overrides={(1, 1): (5, 8, 12, 3)})
+  np.testing.assert_array_equal(canvas, g['c_canvas'])
+  np.testing.assert_array_equal(covered, g['c_covered'])
+  for k in keys:
+    x0, y0, w = wt[k]
+    assert [x0, y0] == g[f'c_pos_{k[0]}{k[1]}'].tolist()
+    np.testing.assert_array_equal(w, g[f'c_warped_{k[0]}{k[1]}'])
+  # without the extras only two values come back
+  assert len(warp.render_tiles(tiles, maps, stride=(20, 20), margin=10)) == 2
+  with pytest.raises(NotImplementedError):
+    warp.render_tiles(tiles, maps, stride=(20, 10))

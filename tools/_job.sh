@@ -1,4 +1,5 @@
-timeout 300 python -m pytest tests/test_warp_cv_gpu.py -x -q 2>&1 | tail -3
-for m in lanczos linear nearest; do
-  timeout 300 python tools/bench_warp.py --interpolation $m --cpu-sections 1 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['config']['workload'][-8:], d['kernel_ms'], d['value'], d['e2e']['value'], d['cpu_baseline'])"
+for m in lanczos nearest; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:remap_kernel -s 2 -c 1 \
+  -o gpurun_out/ncu_r2_warp_$m -f python tools/bench_warp.py --sections 4 --steps 1 --warmup 1 --cpu-sections 0 --interpolation $m > gpurun_out/ncu_warp.log 2>&1
 done
+ls -la gpurun_out/*.ncu-rep | tail -3
