@@ -1,6 +1,8 @@
 """Warping processors (reference processor/warp.py).
 
-`WarpByMap` (processor/warp.py:346-538) renders a subvolume through an inverse coordinate
+`StitchAndRender3dTiles` (processor/warp.py:38-343) renders a grid of 3-d tiles through their
+solved meshes with distance-weighted blending (`warp.ndimage_warp` on the GPU; the blend
+accumulators stay on the device).  `WarpByMap` (processor/warp.py:346-538) renders a subvolume through an inverse coordinate
 map with `warp.warp_subvolume`; its `Config` is the EM-2D pipeline's `warp_config`
 (processor/defaults/em_2d.py:244-262).  Volume I/O goes through the same hooks as the other
 processors of this package (`_open_volume`, `_build_mask`): the connectomics volume stack is
@@ -22,6 +24,187 @@ from ..compat import config as cfg_lib
 
 BoundingBox = compat.BoundingBox
 Subvolume = compat.Subvolume
+
+
+def _border_distance(mask: np.ndarray) -> np.ndarray:
+  """Euclidean distance of every True pixel to the nearest False pixel, with everything
+  outside the array counting as False -- `edt.edt(mask, black_border=True)` of the un-vendored
+  `edt` package the reference calls (processor/warp.py:165), float32 like it."""
+  from scipy import ndimage  # pylint: disable=g-import-not-at-top
+  padded = np.pad(mask.astype(bool), 1)
+  return ndimage.distance_transform_edt(padded)[1:-1, 1:-1].astype(np.float32)
+
+
+class StitchAndRender3dTiles(compat.SubvolumeProcessor):
+  """Renders a volume by warping 3-d tiles through their meshes and blending them
+  (processor/warp.py:38-343).
+
+  The tile meshes are shared by all instances, like the reference's class-level cache;
+  `reset_cache()` drops them.  `tile_mesh_path` is an .npz path or any mapping with
+  'key_to_idx' ({(x, y): column of 'x'}) and 'x' ([3, n_tiles, mz, my, mx] relative meshes).
+  """
+
+  _tile_meshes = None
+  _tile_idx_to_xy = None
+  _tile_boxes: dict = {}
+  _inverted_meshes: dict = {}
+
+  crop_at_borders = False
+
+  def __init__(self, *, tile_map, tile_mesh_path, tile_pattern_path, stride, offset=(0, 0, 0),
+               margin: int = 0, work_size=(128, 128, 128), order: int = 1,
+               parallelism: int = 16, input_volinfo=None):
+    del input_volinfo
+    self._tile_map = np.array(tile_map)
+    self._tile_mesh_path = tile_mesh_path
+    self._tile_pattern_path = tile_pattern_path
+    self._stride = stride  # zyx
+    self._offset = offset  # xyz
+    self._margin = margin
+    self._order = order
+    self._parallelism = parallelism
+    self._work_size = work_size
+    self._key_to_idx = {(x, y): tile_id for y, row in enumerate(tile_map)
+                        for x, tile_id in enumerate(row)}
+
+  @classmethod
+  def reset_cache(cls):
+    cls._tile_meshes = None
+    cls._tile_idx_to_xy = None
+    cls._tile_boxes = {}
+    cls._inverted_meshes = {}
+
+  def _open_tile_volume(self, tile_id: int):
+    """Returns a ZYX-shaped array-like with the data of a tile."""
+    raise NotImplementedError('This function needs to be defined in a subclass.')
+
+  def context(self):
+    return (0, 0, 0), (0, 0, 0)
+
+  def _load_meshes(self) -> bool:
+    cls = StitchAndRender3dTiles
+    if cls._tile_meshes is not None:
+      return False
+    data = self._tile_mesh_path
+    if isinstance(data, (str, bytes)) or hasattr(data, '__fspath__'):
+      data = np.load(data, allow_pickle=True)
+    key_to_idx = data['key_to_idx']
+    if isinstance(key_to_idx, np.ndarray):
+      key_to_idx = key_to_idx.item()
+    cls._tile_idx_to_xy = {v: k for k, v in key_to_idx.items()}
+    cls._tile_meshes = np.asarray(data['x'])
+    assert cls._tile_meshes.shape[1] == len(cls._tile_idx_to_xy)
+    return True
+
+  def _collect_tile_boxes(self, tile_shape_zyx):
+    """Global box every tile can render, and its box in mesh nodes
+    (processor/warp.py:118-149)."""
+    cls = StitchAndRender3dTiles
+    meshes = cls._tile_meshes
+    map_box = BoundingBox(start=(0, 0, 0), size=meshes.shape[2:][::-1])
+    sz, sy, sx = self._stride
+    for i in range(meshes.shape[1]):
+      tx, ty = cls._tile_idx_to_xy[i]
+      tg_box = map_utils.outer_box(meshes[:, i, ...], map_box, self._stride)
+      out_box = BoundingBox(
+          start=(tg_box.start[0] * sx + tx * tile_shape_zyx[-1] + self._offset[0],
+                 tg_box.start[1] * sy + ty * tile_shape_zyx[-2] + self._offset[1],
+                 tg_box.start[2] * sz + self._offset[2]),
+          size=(tg_box.size[0] * sx, tg_box.size[1] * sy, tg_box.size[2] * sz))
+      cls._tile_boxes[i] = out_box, tg_box
+
+  def _get_dts(self, shape, tx: int, ty: int) -> np.ndarray:
+    """Blending weight of a tile: distance from its usable area's edge
+    (processor/warp.py:151-165).  `margin` pixels are ignored on inner edges only."""
+    mask = np.zeros(shape[1:], dtype=bool)
+    if self._margin > 0:
+      x0 = self._margin if tx > 0 else 0
+      x1 = -self._margin if tx < self._tile_map.shape[-1] - 1 else -1
+      y0 = self._margin if ty > 0 else 0
+      y1 = -self._margin if ty < self._tile_map.shape[-2] - 1 else -1
+      mask[y0:y1, x0:x1] = 1
+    else:
+      mask[...] = 1
+    return _border_distance(mask)
+
+  def _tile_work(self, box: BoundingBox, tile_shape_zyx):
+    """Work items of the tiles that reach into `box` (processor/warp.py:167-255): inverse
+    mesh (cached), the part of the box the tile covers, the tile data needed for it."""
+    cls = StitchAndRender3dTiles
+    meshes = cls._tile_meshes
+    image_box = BoundingBox(start=(0, 0, 0), size=tile_shape_zyx[::-1])
+    map_box = BoundingBox(start=(0, 0, 0), size=meshes.shape[2:][::-1])
+    for i, (out_box, tg_box) in cls._tile_boxes.items():
+      sub_box = out_box.intersection(box)
+      if sub_box is None:
+        continue
+      tx, ty = cls._tile_idx_to_xy[i]
+      if i not in cls._inverted_meshes:
+        # one node of context against rounding; holes can only be outside the hull
+        tg_box = tg_box.adjusted_by(start=(-1, -1, -1), end=(1, 1, 1))
+        inverse = map_utils.invert_map(meshes[:, i, ...], map_box, tg_box, stride=self._stride)
+        inverse = map_utils.fill_missing(inverse, extrapolate=True, interpolate_first=False)
+        cls._inverted_meshes[i] = tg_box, inverse
+      else:
+        tg_box, inverse = cls._inverted_meshes[i]
+      # frame with the source tile at the origin
+      local_out_box = out_box.translate((-tx * tile_shape_zyx[-1] - self._offset[0],
+                                         -ty * tile_shape_zyx[-2] - self._offset[1],
+                                         -self._offset[2]))
+      local_warp_box = sub_box.translate(-out_box.start).translate(local_out_box.start)
+      s = 1.0 / np.array(self._stride)[::-1]
+      local_map_box = local_warp_box.scale(s).adjusted_by(start=(-2, -2, -2), end=(2, 2, 2))
+      local_map_box = local_map_box.intersection(tg_box)
+      if local_map_box is None:
+        continue
+      query = local_map_box.translate(-tg_box.start)
+      assert np.all(query.start >= 0)
+      sub_map = inverse[query.to_slice4d()]
+      data_box = map_utils.outer_box(sub_map, local_map_box, self._stride, 1)
+      data_box = data_box.intersection(image_box)
+      if data_box is None:
+        continue
+      dts = self._get_dts(tile_shape_zyx, tx, ty)
+      sub_dts = dts[data_box.to_slice3d()[1:]][None, ...]
+      sub_dts = np.repeat(sub_dts, data_box.size[2], axis=0)
+      yield i, inverse, tg_box, local_warp_box, sub_box, sub_dts, data_box
+
+  def process(self, subvol: Subvolume):
+    """Distance-weighted average of all tiles that reach into `subvol.bbox`
+    (processor/warp.py:258-343)."""
+    import torch  # pylint: disable=g-import-not-at-top
+    box = subvol.bbox
+    cls = StitchAndRender3dTiles
+    mesh_init = self._load_meshes()
+    volstores = {}
+    for i in range(cls._tile_meshes.shape[1]):
+      volstores[i] = self._open_tile_volume(self._key_to_idx[cls._tile_idx_to_xy[i]])
+    tile_shape_zyx = tuple(next(iter(volstores.values())).shape)
+    if mesh_init or not cls._tile_boxes:
+      self._collect_tile_boxes(tile_shape_zyx)
+    # blend accumulators in float32 on the device
+    shape = tuple(int(v) for v in subvol.data.shape[1:])
+    img = torch.zeros(shape, dtype=torch.float32, device='cuda')
+    norm = torch.zeros(shape, dtype=torch.float32, device='cuda')
+    for i, inverse, tg_box, local_warp_box, sub_box, sub_dts, data_box in self._tile_work(
+        box, tile_shape_zyx):
+      image = np.asarray(volstores[i][data_box.to_slice3d()])
+      kwargs = dict(work_size=self._work_size, overlap=(0, 0, 0), image_box=data_box,
+                    map_box=tg_box, out_box=local_warp_box, parallelism=self._parallelism)
+      if image.dtype in (np.uint8, np.float32):
+        image = torch.from_numpy(np.ascontiguousarray(image)).cuda()
+      warped = warp.ndimage_warp(image, inverse, self._stride, order=self._order, **kwargs)
+      if not torch.is_tensor(warped):
+        warped = torch.from_numpy(warped.astype(np.float32)).cuda()
+      weight = warp.ndimage_warp(torch.from_numpy(sub_dts).cuda(), inverse, self._stride,
+                                 **kwargs)
+      sel = sub_box.translate(-box.start).to_slice3d()
+      img[sel] += warped * weight
+      norm[sel] += weight
+    filled = norm > 0
+    img[filled] /= norm[filled]
+    out = img.cpu().numpy().astype(self.output_type(subvol.data.dtype))
+    return self.crop_box_and_data(box, out[None, ...])
 
 
 class WarpByMap(compat.SubvolumeProcessor):
