@@ -127,6 +127,15 @@ class StitchAndRender3dTiles(compat.SubvolumeProcessor):
       mask[...] = 1
     return _border_distance(mask)
 
+  def _dts_on_device(self, shape, tx: int, ty: int):
+    """`_get_dts` of a tile, computed once per instance and kept on the device."""
+    import torch  # pylint: disable=g-import-not-at-top
+    cache = self.__dict__.setdefault('_dts_cache', {})
+    key = (tuple(shape[1:]), tx, ty)
+    if key not in cache:
+      cache[key] = torch.from_numpy(self._get_dts(shape, tx, ty)).cuda()
+    return cache[key]
+
   def _tile_work(self, box: BoundingBox, tile_shape_zyx):
     """Work items of the tiles that reach into `box` (processor/warp.py:167-255): inverse
     mesh (cached), the part of the box the tile covers, the tile data needed for it."""
@@ -164,9 +173,10 @@ class StitchAndRender3dTiles(compat.SubvolumeProcessor):
       data_box = data_box.intersection(image_box)
       if data_box is None:
         continue
-      dts = self._get_dts(tile_shape_zyx, tx, ty)
-      sub_dts = dts[data_box.to_slice3d()[1:]][None, ...]
-      sub_dts = np.repeat(sub_dts, data_box.size[2], axis=0)
+      # the 2-d weight repeated over the sections of the data box (on the device)
+      dts = self._dts_on_device(tile_shape_zyx, tx, ty)
+      sub_dts = dts[data_box.to_slice3d()[1:]][None, ...].expand(
+          int(data_box.size[2]), -1, -1).contiguous()
       yield i, inverse, tg_box, local_warp_box, sub_box, sub_dts, data_box
 
   def process(self, subvol: Subvolume):
@@ -196,14 +206,17 @@ class StitchAndRender3dTiles(compat.SubvolumeProcessor):
       warped = warp.ndimage_warp(image, inverse, self._stride, order=self._order, **kwargs)
       if not torch.is_tensor(warped):
         warped = torch.from_numpy(warped.astype(np.float32)).cuda()
-      weight = warp.ndimage_warp(torch.from_numpy(sub_dts).cuda(), inverse, self._stride,
-                                 **kwargs)
+      weight = warp.ndimage_warp(sub_dts, inverse, self._stride, **kwargs)
       sel = sub_box.translate(-box.start).to_slice3d()
       img[sel] += warped * weight
       norm[sel] += weight
     filled = norm > 0
     img[filled] /= norm[filled]
-    out = img.cpu().numpy().astype(self.output_type(subvol.data.dtype))
+    out_dtype = np.dtype(self.output_type(subvol.data.dtype))
+    if out_dtype == np.uint8:  # same truncation as astype, 4x less to copy back
+      out = img.clamp_(0, 255).to(torch.uint8).cpu().numpy()
+    else:
+      out = img.cpu().numpy().astype(out_dtype)
     return self.crop_box_and_data(box, out[None, ...])
 
 

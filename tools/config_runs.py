@@ -245,6 +245,37 @@ def config5(args):
   res['warp_voxels_per_s'] = nvox / res['warp_seconds']
   res['problem_seconds'] = (res['flow_seconds'] + res['filter_seconds'] + res['mesh_seconds'] +
                             res['warp_seconds'])
+  if args.render:
+    # the notebook's last step: StitchAndRender3dTiles over 512^3 boxes of the stitched volume
+    from sofima_b200 import compat
+    from sofima_b200.processor import warp as pwarp
+    tile_ids = {key: 100 + idx for key, idx in key_to_idx.items()}
+    by_id = {tid: tiles[key][0] for key, tid in tile_ids.items()}
+
+    class Renderer(pwarp.StitchAndRender3dTiles):
+      def _open_tile_volume(self, tile_id):
+        return by_id[tile_id]
+
+    Renderer.reset_cache()
+    tile_map = [[tile_ids[tx, ty] for tx in range(nt)] for ty in range(nt)]
+    r = Renderer(tile_map=tile_map, tile_pattern_path='{tile_id}', stride=stride,
+                 tile_mesh_path={'key_to_idx': key_to_idx, 'x': np.asarray(x)},
+                 offset=(0, 0, 0))
+    full = compat.BoundingBox(start=(0, 0, 0), size=(nt * stepxy, nt * stepxy, nz))
+    stitched = np.zeros(full.size[::-1], np.uint8)
+    t0 = time.perf_counter()
+    for y0 in range(0, int(full.size[1]), 512):
+      for x0 in range(0, int(full.size[0]), 512):
+        b = compat.BoundingBox(start=(x0, y0, 0), end=(min(x0 + 512, full.size[0]),
+                                                       min(y0 + 512, full.size[1]), nz))
+        sv = r.process(compat.Subvolume(np.zeros((1,) + tuple(b.size[::-1]), np.uint8), b))
+        stitched[sv.bbox.to_slice3d()] = sv.data[0]
+    torch.cuda.synchronize()
+    res['render_seconds'] = time.perf_counter() - t0
+    res['render_voxels_per_s'] = stitched.size / res['render_seconds']
+    res['render_filled_fraction'] = float((stitched > 0).mean())
+    res['problem_seconds'] += res['render_seconds']
+    Renderer.reset_cache()
   res['extrapolated_32_problems_on_8_gpus_seconds'] = res['problem_seconds'] * 32 / 8
   print(json.dumps(res))
 
@@ -257,6 +288,7 @@ if __name__ == '__main__':
   ap.add_argument('--tiles', type=int, default=3)
   ap.add_argument('--depth', type=int, default=64)
   ap.add_argument('--mesh-max-iters', type=int, default=20000)
+  ap.add_argument('--render', action='store_true')
   a = ap.parse_args()
   if a.which == 'config4':
     a.size = a.size or 8192
