@@ -1,7 +1,7 @@
 """Multi-GPU check of the row-sharded mesh (launch with torchrun, one rank per GPU):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-      --master-port 29511 tests/multi/run_sharded_mesh.py [ny nx iters]
+      --master-port 29511 tests/multi/run_sharded_mesh.py [ny nx iters sections]
 
 Every rank relaxes its slab with relax_mesh_sharded; rank 0 also solves the whole
 mesh on its own GPU with mesh.relax_mesh and compares (bit-exact expected).  Prints
@@ -24,12 +24,13 @@ def main():
   ny = int(sys.argv[1]) if len(sys.argv) > 1 else 512
   nx = int(sys.argv[2]) if len(sys.argv) > 2 else 384
   iters = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+  nz = int(sys.argv[4]) if len(sys.argv) > 4 else 2
   local = int(os.environ.get('LOCAL_RANK', '0'))
   torch.cuda.set_device(local)
   dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   rank, world = dist.get_rank(), dist.get_world_size()
   rng = np.random.default_rng(5)
-  shape = (2, 2, ny, nx)
+  shape = (2, nz, ny, nx)
   prev = (rng.standard_normal(shape) * 4).astype(np.float32)
   prev[rng.random(shape) < 0.01] = np.nan
   x0 = np.zeros(shape, np.float32)
@@ -46,7 +47,7 @@ def main():
   torch.cuda.synchronize()
   dist.barrier()
   t_sharded = time.perf_counter() - t0
-  slabs = [torch.empty((2, 2, b - a, nx), device='cuda') for a, b in
+  slabs = [torch.empty((2, nz, b - a, nx), device='cuda') for a, b in
            mesh_sharded.partition_rows(ny, world)]
   dist.all_gather(slabs, got.contiguous())
   ok, t_single, err = True, None, 0.0
