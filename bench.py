@@ -832,6 +832,49 @@ def run_ours(args):
                          'sample': 'one 1024^2 crop, oracle/warp_oracle.py (NumPy float64, '
                                    '== scipy.ndimage.map_coordinates)'}}
     del wimg
+    # f-3 warp.warp_subvolume: 4 sections of 4096^2 uint8 through a smooth map (stride 32),
+    # Lanczos-4 (the reference's default); device sections in / out.
+    from sofima_b200 import compat as compat_mod
+    from oracle import warp_cv_oracle
+    sv_img = rngw.integers(0, 256, (1, 4, 4096, 4096), dtype=np.uint8)
+    sv_map = np.stack([ndi.gaussian_filter(rngw.standard_normal((4, 129, 129)), (0, 3, 3)) * 60
+                       for _ in range(2)])
+    sv_box = compat_mod.BoundingBox(start=(0, 0, 0), size=(4096, 4096, 4))
+    sv_mbox = compat_mod.BoundingBox(start=(0, 0, 0), size=(129, 129, 4))
+    sv_dev = torch.from_numpy(sv_img).to(dev)
+    sf = lambda i: warp_mod.warp_subvolume(sv_dev, sv_box, sv_map, sv_mbox, 32, sv_box)
+    for i in range(W):
+      sv_out = sf(i)
+    ctx.set_timing(True)
+    sv_ms, _ = timed(sf, 10)
+    sv_rep = ctx.timing_report()
+    ctx.set_timing(False)
+    sv_kernel_ms = sv_rep['warp_subvolume']['ms'] / sv_rep['warp_subvolume']['n']
+    sv_gbs = 2 * sv_img.size / (sv_kernel_ms * 1e-3) / 1e9
+    entry = {
+        'workload': 'warp.warp_subvolume, 4 sections of 4096^2 uint8, 129^2-node map (stride '
+                    '32), Lanczos-4 (scipy grid interpolation + OpenCV convertMaps / remap '
+                    'semantics), device sections in / out',
+        'value': sv_img.size / (sv_ms / 10 * 1e-3), 'unit': 'pixels/s',
+        'ms_per_call': sv_ms / 10, 'kernel_ms': sv_kernel_ms,
+        'roofline': {'bound': 'hbm', 'achieved': sv_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': sv_gbs / peaks['hbm_gbs'], 'traffic': None,
+                     'peak_source': peaks['source'], 'algorithmic_bytes_per_pixel': 2,
+                     'note': '64 taps per pixel served by L1 / L2: bound by load issue and '
+                             'latency, not HBM (profiles/ncu_r2_warp_lanczos.txt)'}}
+    try:
+      t0 = time.perf_counter()
+      sv_ref = warp_cv_oracle.reference_pipeline(sv_img[:, :1], sv_map[:, :1], 32, 'lanczos')
+      sv_cpu = sv_ref.size / (time.perf_counter() - t0)
+      entry['cpu_baseline'] = {
+          'value': sv_cpu, 'unit': 'pixels/s', 'cores': 1, 'kind': 'reference',
+          'sample': 'one of the sections: the scipy + cv2 calls of warp.py:144-165 with the '
+                    'real libraries',
+          'identical_to_gpu': bool(np.array_equal(sv_ref, sv_out[:, :1].cpu().numpy()))}
+    except ImportError as e:
+      entry['cpu_baseline'] = {'unavailable': str(e)}
+    widened['warp_subvolume'] = entry
+    del sv_dev, sv_out
     result['widened'] = widened
 
   # ---------------- CPU baseline (rank 0, N = 1 only) ----------------

@@ -279,3 +279,38 @@ def warp_subvolume(image, image_box, coord_map, map_box, stride, out_box, interp
   if back is not None:
     return back[warped]
   return warped.astype(orig_dtype)
+
+
+def reference_pipeline(image, coord_map, stride, interpolation='lanczos', threads=1):
+  """The reference's per-section calls (warp.py:123-165) with the REAL scipy and cv2, for
+  boxes that all start at the origin and cover the image: the CPU baseline of the warp path
+  (bench.py, tools/bench_warp.py) and a full-size cross-check.  Raises ImportError without
+  cv2."""
+  import cv2 as cv  # pylint: disable=g-import-not-at-top
+  from concurrent import futures  # pylint: disable=g-import-not-at-top
+  from scipy import interpolate  # pylint: disable=g-import-not-at-top
+  flag = {'nearest': cv.INTER_NEAREST, 'linear': cv.INTER_LINEAR, 'cubic': cv.INTER_CUBIC,
+          'lanczos': cv.INTER_LANCZOS4}[interpolation]
+  n, nz, h, w = image.shape
+  gy, gx = np.mgrid[:coord_map.shape[2], :coord_map.shape[3]]
+  abs_map = coord_map.copy()
+  abs_map[0] += gx * stride
+  abs_map[1] += gy * stride
+  pts = (np.arange(coord_map.shape[2]) * float(stride),
+         np.arange(coord_map.shape[3]) * float(stride))
+  out = np.zeros_like(image)
+  oy, ox = np.mgrid[:h, :w]
+
+  def section(z):
+    dx = interpolate.RegularGridInterpolator(pts, abs_map[0, z], bounds_error=False,
+                                             fill_value=None)((oy, ox)).astype(np.float32)
+    dy = interpolate.RegularGridInterpolator(pts, abs_map[1, z], bounds_error=False,
+                                             fill_value=None)((oy, ox)).astype(np.float32)
+    m1, m2 = cv.convertMaps(dx, dy, dstmap1type=cv.CV_16SC2,
+                            nninterpolation=(flag == cv.INTER_NEAREST))
+    for c in range(n):
+      out[c, z] = cv.remap(image[c, z], m1, m2, interpolation=flag)
+
+  with futures.ThreadPoolExecutor(max_workers=threads) as ex:
+    list(ex.map(section, range(nz)))
+  return out

@@ -31,32 +31,8 @@ def make_case(nz, size, stride, seed=0):
 
 def cpu_pipeline(img, cmap, stride, inter, threads):
   """The reference's per-section work with the real libraries (warp.py:123-165)."""
-  import cv2 as cv
-  from concurrent import futures
-  from scipy import interpolate
-  flag = {'nearest': cv.INTER_NEAREST, 'linear': cv.INTER_LINEAR, 'cubic': cv.INTER_CUBIC,
-          'lanczos': cv.INTER_LANCZOS4}[inter]
-  _, nz, h, w = img.shape
-  gy, gx = np.mgrid[:cmap.shape[2], :cmap.shape[3]]
-  abs_map = cmap.copy()
-  abs_map[0] += gx * stride
-  abs_map[1] += gy * stride
-  pts = (np.arange(cmap.shape[2]) * float(stride), np.arange(cmap.shape[3]) * float(stride))
-  out = np.zeros_like(img)
-  oy, ox = np.mgrid[:h, :w]
-
-  def section(z):
-    dx = interpolate.RegularGridInterpolator(pts, abs_map[0, z], bounds_error=False,
-                                             fill_value=None)((oy, ox)).astype(np.float32)
-    dy = interpolate.RegularGridInterpolator(pts, abs_map[1, z], bounds_error=False,
-                                             fill_value=None)((oy, ox)).astype(np.float32)
-    m1, m2 = cv.convertMaps(dx, dy, dstmap1type=cv.CV_16SC2,
-                            nninterpolation=(flag == cv.INTER_NEAREST))
-    out[0, z] = cv.remap(img[0, z], m1, m2, interpolation=flag)
-
-  with futures.ThreadPoolExecutor(max_workers=threads) as ex:
-    list(ex.map(section, range(nz)))
-  return out
+  from oracle import warp_cv_oracle
+  return warp_cv_oracle.reference_pipeline(img, cmap, stride, inter, threads)
 
 
 def main():
