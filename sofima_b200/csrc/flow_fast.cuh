@@ -54,6 +54,18 @@ __device__ __forceinline__ void stage_twiddles(float2* tw_s, const float2* __res
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(tw + i) : "memory");
   }
 }
+// The same table as the inverse-row kernel reads it -- thread (f, k1) needs W^(k1 n2) for all
+// n2 -- transposed to [n2][k1]: the 16 lanes of a half-warp then read 16 consecutive entries
+// instead of a stride of n2 (a 16-way bank conflict for n2 = 16).
+template <int N2, int NT>
+__device__ __forceinline__ void stage_twiddles_by_n2(float2* tw_s, const float2* __restrict__ tw) {
+  for (int i = threadIdx.x; i < N2 * kN1; i += NT) {
+    const int n2 = i / kN1, k1 = i - n2 * kN1;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(tw_s + i);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(tw + k1 * n2)
+                 : "memory");
+  }
+}
 __device__ __forceinline__ void stage_twiddles_wait() {
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
@@ -473,7 +485,7 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
   if (2 * rp0 >= P.sy) return;
   constexpr int NKX = L / 2 + 1;
   const float2* Ub = U + (size_t)blockIdx.z * P.sy * NKX;
-  stage_twiddles<L, NT>(tw_s, tw);  // needed after the first DFT pass
+  stage_twiddles_by_n2<N2, NT>(tw_s, tw);  // needed after the first DFT pass
   const int f = threadIdx.x / kN1, k1 = threadIdx.x % kN1;
   const int y = 2 * (rp0 + f);
   const bool line = threadIdx.x < TR * kN1 && y < P.sy;  // thread (f, k1) of a real row
@@ -523,7 +535,7 @@ rows_inv_fast(Problem P, const float2* __restrict__ tw, const float2* __restrict
   if (line) {
 #pragma unroll
     for (int n2 = 0; n2 < N2; ++n2)
-      ex[f * D::EXR + k1 * D::N2P + n2] = cmul(bq[n2], tw_s[k1 * n2]);
+      ex[f * D::EXR + k1 * D::N2P + n2] = cmul(bq[n2], tw_s[n2 * kN1 + k1]);
   }
   __syncthreads();
   unsigned long long best = 0;
