@@ -162,14 +162,52 @@ def config4(args):
 
 
 def config5(args):
+  """One problem per call of `config5_problem`; with --problems P under torch.distributed.run
+  the P independent problems are dealt round-robin to the ranks (no communication) and the
+  job time is the maximum over the ranks."""
+  import torch.distributed as dist
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  mine = list(range(rank, args.problems, world))
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t0 = time.perf_counter()
+  results = [config5_problem(args, dev, seed=5 + 17 * k) for k in mine]
+  torch.cuda.synchronize()
+  mine_s = time.perf_counter() - t0
+  if world > 1:
+    t = torch.tensor([mine_s], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    job_s = float(t.item())
+  else:
+    job_s = mine_s
+  if rank == 0:
+    res = dict(results[0])
+    if args.problems > 1:
+      res.update(problems=args.problems, n_gpus=world, job_seconds=job_s,
+                 problems_per_rank=len(mine),
+                 per_problem_seconds_rank0=[r['problem_seconds'] for r in results],
+                 note='job_seconds = max over ranks of the wall time for its problems '
+                      '(synthetic tiles are generated outside the per-stage timers but inside '
+                      'job_seconds)')
+    print(json.dumps(res))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def config5_problem(args, dev, seed=5):
   from sofima_b200 import flow_utils, mesh, stitch_elastic, warp
-  dev = torch.device('cuda', 0)
-  torch.cuda.set_device(0)
   nt, n, nz = args.tiles, args.size, args.depth
   ov = int(n * 0.1)
   stepxy = n - ov
-  rng = np.random.default_rng(5)
-  big = smooth_texture((nz + 16, (nt - 1) * stepxy + n + 64, (nt - 1) * stepxy + n + 64), 1.5, 5, dev)
+  rng = np.random.default_rng(seed)
+  big = smooth_texture((nz + 16, (nt - 1) * stepxy + n + 64, (nt - 1) * stepxy + n + 64), 1.5, seed, dev)
   tiles, pos = {}, {}
   for ty in range(nt):
     for tx in range(nt):
@@ -277,7 +315,7 @@ def config5(args):
     res['problem_seconds'] += res['render_seconds']
     Renderer.reset_cache()
   res['extrapolated_32_problems_on_8_gpus_seconds'] = res['problem_seconds'] * 32 / 8
-  print(json.dumps(res))
+  return res
 
 
 if __name__ == '__main__':
@@ -289,6 +327,7 @@ if __name__ == '__main__':
   ap.add_argument('--depth', type=int, default=64)
   ap.add_argument('--mesh-max-iters', type=int, default=20000)
   ap.add_argument('--render', action='store_true')
+  ap.add_argument('--problems', type=int, default=1)
   a = ap.parse_args()
   if a.which == 'config4':
     a.size = a.size or 8192
