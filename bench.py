@@ -492,7 +492,7 @@ def run_ours(args):
                        'tensor_pipe_pct': round(a['tensor_pipe_pct_max'], 1)}
 
     # sustained: the same step repeated for at least two seconds (clocks settle under load)
-    n_sust = max(K, int(np.ceil(2000.0 / (ms / K))))
+    n_sust = max(K, int(np.ceil(2100.0 / (ms / K))))  # 5 % margin: never under 2 s
     with ClockSampler(local) as cs2:
       ms_sust, _ = timed(flow_step, n_sust)
     sustained = {'value': world * pairs_per_step * n_sust / (ms_sust * 1e-3),

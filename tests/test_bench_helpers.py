@@ -33,7 +33,7 @@ def test_committed_bench_lines_follow_the_contract():
   contract names -- a guard against dropping one while editing bench.py."""
   import os
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  line = json.load(open(os.path.join(root, 'profiles', 'bench_r1_l.json')))
+  line = json.load(open(os.path.join(root, 'profiles', 'bench_r2_default.json')))
   for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
               'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'clocks',
               'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
@@ -48,6 +48,14 @@ def test_committed_bench_lines_follow_the_contract():
   mesh = line['mesh']
   assert mesh['roofline']['bound'] == 'hbm' and 0 < mesh['roofline']['frac'] < 1
   assert mesh['cpu_baseline']['kind'] == 'port'
-  ref = json.load(open(os.path.join(root, 'profiles', 'bench_r1_l_reference_arm.json')))
+  assert line['roofline']['bound'] == 'hbm' and 0 < line['roofline']['frac'] < 1
+  assert line['roofline']['traffic'] > line['roofline']['algorithmic_io_bytes_per_step']
+  assert line['sustained']['seconds'] >= 1.99  # (bench.py now aims at 2.1 s)
+  ref = json.load(open(os.path.join(root, 'profiles', 'bench_r2_reference_arm.json')))
   assert ref['impl'] == 'reference' and ref['metric'] == line['metric']
   assert ref['e2e']['h2d_bytes_per_step'] == 0 and ref['cpu_baseline']['value'] == ref['value']
+  # multi-GPU lines carry the in-run parity record of the sharded mesh
+  for n in (2, 4, 8):
+    multi = json.load(open(os.path.join(root, 'profiles', f'bench_r2_n{n}_gpus.json')))
+    assert multi['n_gpus'] == n and multi['mesh']['parity']['bit_identical'] is True
+    assert multi['mesh']['parity']['max_abs_err'] == 0.0
