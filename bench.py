@@ -599,11 +599,14 @@ def run_ours(args):
     rep = ctx.timing_report()
     ctx.set_timing(False)
     step_ms = max_over_ranks(rep['mesh_step']['ms'] / rep['mesh_step']['n'])
-    if world > 1:
-      # a sharded step kernel also waits for its neighbours' flags, and CUDA events around a
-      # single launch then include the skew between the ranks: the launch can never take
-      # longer than the step of the timed region, which is what bounds it here
-      step_ms = min(step_ms, ms / K / iters)
+    step_ms_events = step_ms
+    # The per-launch events serialise what the solver overlaps: on one GPU the one-block kernel
+    # that adds the FIRE partial sums runs behind the step with programmatic dependent launch
+    # and the next step's loads start under it (events between the launches switch that off);
+    # a sharded step kernel also waits for its neighbours' flags, and events around a single
+    # launch then include the skew between the ranks.  A launch can never take longer than
+    # the step of the timed region, which is what bounds it here.
+    step_ms = min(step_ms, ms / K / iters)
     local_nodes = (y1 - y0) * MESH_N
     achieved = local_nodes * MESH_BYTES_PER_UPDATE / (step_ms * 1e-3) / 1e9
     mtraffic, mtraffic_src = _step_traffic('mesh')
@@ -671,7 +674,13 @@ def run_ours(args):
                      'kernel': 'mesh2d_kernel<1,true,%s>' % ('true' if world > 1 else 'false'),
                      'kernel_us_per_launch': step_ms * 1e3,
                      'algorithmic_bytes_per_launch': local_nodes * MESH_BYTES_PER_UPDATE,
-                     'note': 'per-GPU: bytes of the rank-local slab / its launch time'},
+                     'kernel_us_per_launch_serialised': step_ms_events * 1e3,
+                     'note': 'per-GPU: bytes of the rank-local slab / its launch time; the launch '
+                             'time is the smaller of (a) CUDA events around each launch in a '
+                             'separate chunk, which serialise the step and its one-block FIRE '
+                             'reduce kernel (kernel_us_per_launch_serialised), and (b) the '
+                             'device time of the timed chunk / its steps, an upper bound of the '
+                             'step kernel inside the pipelined solve'},
         'e2e': {'value': nodes * iters * K / (e2e_ms * 1e-3),
                 'unit': 'node-updates/s',
                 'h2d_bytes_per_step': 2 * 2 * local_nodes * 4,

@@ -39,6 +39,10 @@ template <int SRC>
 __global__ void __launch_bounds__(kThreads)
 stitch_target2d_kernel(const Params p, const StitchParams q, int fire, float* out,
                        float2* outp) {
+  if (SRC == 2) {  // inside the step loop: may be launched early behind the FIRE reduce kernel
+    grid_dep_wait();
+    grid_dep_launch();
+  }
   const int t = blockIdx.y;
   const int node = blockIdx.x * kThreads + threadIdx.x;
   const int my = q.my, mx = q.mx;
@@ -259,6 +263,10 @@ struct StitchParams3 {
 template <int SRC>
 __global__ void __launch_bounds__(kThreads)
 stitch_target3d_kernel(const Params p, const StitchParams3 q, int fire, float* out) {
+  if (SRC == 2) {  // inside the step loop: may be launched early behind the FIRE reduce kernel
+    grid_dep_wait();
+    grid_dep_launch();
+  }
   const int t = blockIdx.y;
   const long long tile_nodes = (long long)q.m[0] * q.m[1] * q.m[2];
   const long long node = (long long)blockIdx.x * kThreads + threadIdx.x;

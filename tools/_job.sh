@@ -1,2 +1,9 @@
-timeout 850 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 tools/config_runs.py config5 --depth 128 --render --problems 32 > gpurun_out/config5_r2_n8.json 2> gpurun_out/config5_r2_n8.err
-grep '^{' gpurun_out/config5_r2_n8.json | tail -1 | cut -c1-2500; tail -3 gpurun_out/config5_r2_n8.err
+timeout 900 python -m pytest tests/test_mesh_gpu.py tests/test_stitch_gpu.py tests/test_relax_mesh_proc_gpu.py tests/test_pipeline_gpu.py tests/test_fullsize_parity_gpu.py tests/test_tile_mesh_gpu.py -x -q 2>&1 | tail -3
+timeout 200 python /dev/stdin <<'PY' 2>&1 | cut -c1-140
+import sys, os, json
+sys.path.insert(0, os.getcwd() + '/tools'); sys.path.insert(0, os.getcwd())
+import dev_mesh_bench as d
+d.run(2048, 1, 1000, True, True)
+d.run(102, 16, 1000, True, True)
+PY
+timeout 300 python tools/stitch_bench.py 2>&1 | tail -4 | cut -c1-300
