@@ -118,7 +118,24 @@ def _to_device(a, ctx: _native.Context, copy: bool):
 
 
 def _from_device(t, like):
-  return t if _is_tensor(like) else t.cpu().numpy()
+  if _is_tensor(like):
+    return t
+  return _to_host(t)
+
+
+def _to_host(t):
+  """CUDA tensor -> NumPy array."""
+  nbytes = t.numel() * t.element_size()
+  if (1 << 20) <= nbytes <= (1 << 30):
+    # Read back through torch's caching pinned-host allocator: a pageable destination costs a
+    # bounce copy plus a page fault per 4 KB of fresh memory (14 ms for a 2048^2 mesh against
+    # 0.7 ms of DMA).  The array keeps the pinned block alive; it returns to the cache when
+    # the caller drops the array.
+    torch = _torch()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t)
+    return host.numpy()
+  return t.cpu().numpy()
 
 
 def _shape_pod(shape: Sequence[int], kind: int) -> _native.MeshShape:

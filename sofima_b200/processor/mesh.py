@@ -331,7 +331,7 @@ class RelaxMesh(compat.SubvolumeProcessor):
     folded = mask_irregular(sec, integration_config.stride, cfg.mesh_min_frac,
                             dilation_iters=5)
     if not bool(folded.any()):
-      return first.cpu().numpy(), e_kin, steps, SolutionStatus.REGULAR
+      return mesh_lib._to_host(first), e_kin, steps, SolutionStatus.REGULAR
     xd[:, 0] = sec
 
     logging.info('Attempting relaxation with 10% k0.')
@@ -342,13 +342,13 @@ class RelaxMesh(compat.SubvolumeProcessor):
     xd, _, prep_steps = mesh_lib.relax_mesh(to_dev(start), xd, soft)
     sec = xd[:, 0].contiguous()
     if bool(mask_irregular(sec, integration_config.stride, cfg.mesh_min_frac).any()):
-      return first.cpu().numpy(), e_kin, steps + prep_steps, SolutionStatus.PREP_FAILED
+      return mesh_lib._to_host(first), e_kin, steps + prep_steps, SolutionStatus.PREP_FAILED
     xd[:, 0] = sec
 
     if mask is not None:
       xd[:, torch.from_numpy(np.ascontiguousarray(mask)).to(dev)] = float('nan')
     xd, e_kin2, reg_steps = mesh_lib.relax_mesh(xd, pd, integration_config)
-    return (xd.cpu().numpy(), e_kin2, steps + prep_steps + reg_steps,
+    return (mesh_lib._to_host(xd), e_kin2, steps + prep_steps + reg_steps,
             SolutionStatus.REGULARIZED)
 
   def run_relaxation(self, bbox):

@@ -19,6 +19,7 @@ import numpy as np
 
 from .. import compat
 from .. import map_utils
+from .. import mesh as _mesh_lib
 from .. import warp
 from ..compat import config as cfg_lib
 
@@ -214,7 +215,7 @@ class StitchAndRender3dTiles(compat.SubvolumeProcessor):
     img[filled] /= norm[filled]
     out_dtype = np.dtype(self.output_type(subvol.data.dtype))
     if out_dtype == np.uint8:  # same truncation as astype, 4x less to copy back
-      out = img.clamp_(0, 255).to(torch.uint8).cpu().numpy()
+      out = _mesh_lib._to_host(img.clamp_(0, 255).to(torch.uint8))
     else:
       out = img.cpu().numpy().astype(out_dtype)
     return self.crop_box_and_data(box, out[None, ...])

@@ -134,7 +134,7 @@ def ndimage_warp(image, coord_map: np.ndarray, stride: Sequence[float],
   _native.check(ctx.handle, rc)
   if _mesh._is_tensor(image):
     return out_d.view(img_d.dtype).reshape(out_shape)
-  warped = out_d.cpu().numpy().view(np_dtype).reshape(out_shape)
+  warped = _mesh._to_host(out_d).view(np_dtype).reshape(out_shape)
   if labels_back is not None:
     warped = labels_back[warped]
   return warped
