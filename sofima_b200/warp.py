@@ -273,11 +273,22 @@ def warp_subvolume(image, image_box, coord_map, map_box, stride, out_box, interp
   # Host arrays: blocks of sections travel through two pairs of pinned buffers, so that the
   # host copies of one block overlap the transfers and the kernel of the previous one.
   n, nz = out_shape[0], out_shape[1]
-  warped = np.empty(out_shape, np_dtype)
+  out_bytes_total = int(np.prod(out_shape)) * np_dtype.itemsize
+  # The result lives in pinned memory from torch's caching host allocator when it is not
+  # huge: the device writes every block straight into it (no bounce copy, no page faults on
+  # fresh pageable memory).  The array keeps the block alive until the caller drops it.
+  direct = 0 < out_bytes_total <= (1 << 30)
+  if direct:
+    warped_t = torch.empty(out_bytes_total, dtype=torch.uint8, pin_memory=True)
+    warped = warped_t.numpy().view(np_dtype).reshape(out_shape)
+  else:
+    warped_t = None
+    warped = np.empty(out_shape, np_dtype)
   in_sec = n * image.shape[2] * image.shape[3] * np_dtype.itemsize
   out_sec = n * out_shape[2] * out_shape[3] * np_dtype.itemsize
   zc = max(1, min(nz, _BLOCK_BYTES // max(in_sec, out_sec, 1)))
-  pins = _pinned_blocks(zc * in_sec, zc * out_sec)
+  pins = _pinned_blocks(zc * in_sec, 0 if direct else zc * out_sec)
+  chan_out = out_shape[2] * out_shape[3] * np_dtype.itemsize  # bytes of one section, 1 channel
   pending = None  # (z0, z1, pinned out view, event, keep-alive)
   for k, z0 in enumerate(range(0, nz, zc)):
     z1 = min(nz, z0 + zc)
@@ -290,16 +301,26 @@ def warp_subvolume(image, image_box, coord_map, map_box, stride, out_box, interp
     img_d = src.to(device, non_blocking=True)
     out_d = torch.empty((z1 - z0) * out_sec, dtype=torch.uint8, device=device)
     keep = launch(img_d, z0, z1, out_d)
-    dst = pin_out[:(z1 - z0) * out_sec]
-    dst.copy_(out_d, non_blocking=True)
+    if direct:
+      for c in range(n):  # [c, z0:z1] is contiguous in the result
+        o = (c * nz + z0) * chan_out
+        warped_t[o:o + (z1 - z0) * chan_out].copy_(
+            out_d[c * (z1 - z0) * chan_out:(c + 1) * (z1 - z0) * chan_out], non_blocking=True)
+      dst = None
+    else:
+      dst = pin_out[:(z1 - z0) * out_sec]
+      dst.copy_(out_d, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
     done[0] = ev
-    if pending is not None:
+    if pending is not None and not direct:
       _collect(warped, pending, np_dtype)
     pending = (z0, z1, dst, ev, (img_d, out_d, keep))
   if pending is not None:
-    _collect(warped, pending, np_dtype)
+    if direct:
+      pending[3].synchronize()  # the last block (stream order: all earlier ones too)
+    else:
+      _collect(warped, pending, np_dtype)
   if labels_back is not None:
     return labels_back[warped]
   return warped.astype(orig_dtype, copy=False)
@@ -316,6 +337,9 @@ def _pinned_blocks(in_bytes: int, out_bytes: int):
   key = threading.get_ident()
   cur = _PINNED.get(key)
   if cur is None or cur[0][0].numel() < in_bytes or cur[0][1].numel() < out_bytes:
+    if cur is not None:  # keep the larger of the old and new sizes of either buffer
+      in_bytes = max(in_bytes, cur[0][0].numel())
+      out_bytes = max(out_bytes, cur[0][1].numel())
     cur = [(torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True),
             torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True), [None])
            for _ in range(2)]
