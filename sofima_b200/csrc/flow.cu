@@ -1551,12 +1551,26 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
     }
     // transforms over x, y, z of all 2 * nb volumes (forward), then of the nb products.
     auto transform = [&](bool inverse, long long nvol) -> int {
-      struct Axis { const FftPlan* F; long long nlines, inner, istride, ostride, es; };
+      struct Axis {
+        const FftPlan* F;
+        long long nlines, inner, istride, ostride, es;
+        LinePrune pr;
+      };
       const long long plane = (long long)P.Ly * P.Lx;
+      const LinePrune all = {1, 1, 1, 1};
+      // Forward: the patches fill z < pd, y < ph, x < pw of the padded volumes.  The x pass
+      // only has to touch the lines with z < pd and y < ph, the y pass those with z < pd (all
+      // other lines are zero and their transform is zero): 1.75 instead of 3 passes' worth of
+      // traffic for 80^3 patches in 160^3 volumes.  The inverse needs every line.
+      const long long pd = P.img[0].pd > P.img[1].pd ? P.img[0].pd : P.img[1].pd;
+      const long long ph = P.img[0].ph > P.img[1].ph ? P.img[0].ph : P.img[1].ph;
+      const LinePrune px = {P.Lz, pd, P.Ly, ph}, py = {P.Lz, pd, P.Lx, P.Lx};
       const Axis axes[3] = {
-          {&Fx, nvol * P.Lz * P.Ly, 1, 0, P.Lx, 1},                       // x: contiguous lines
-          {&Fy, nvol * P.Lz * P.Lx, P.Lx, 1, plane, P.Lx},                // y: lines (z, x)
-          {&Fz, nvol * plane, plane, 1, vol, plane},                      // z: lines (y, x)
+          {&Fx, inverse ? nvol * P.Lz * P.Ly : nvol * pd * ph, 1, 0, P.Lx, 1,
+           inverse ? all : px},                                           // x: contiguous lines
+          {&Fy, inverse ? nvol * P.Lz * P.Lx : nvol * pd * P.Lx, P.Lx, 1, plane, P.Lx,
+           inverse ? all : py},                                           // y: lines (z, x)
+          {&Fz, nvol * plane, plane, 1, vol, plane, all},                 // z: lines (y, x)
       };
       for (int a = 0; a < 3; ++a) {
         const Axis& A = axes[inverse ? 2 - a : a];
@@ -1566,10 +1580,10 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
         LaunchTimer timer(ctx, "flow3_fft");
         if (inverse)
           axis_fft_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(
-              Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+              Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C, A.pr);
         else
           axis_fft_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(
-              Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+              Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C, A.pr);
         SOFIMA_CHECK_LAUNCH(ctx);
       }
       return SOFIMA_OK;
@@ -1693,10 +1707,10 @@ static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, cons
       LaunchTimer timer(ctx, "flow3_fft");
       if (inverse)
         axis_fft_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(
-            data, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+            data, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C, LinePrune{1, 1, 1, 1});
       else
         axis_fft_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(
-            data, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C);
+            data, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C, LinePrune{1, 1, 1, 1});
       SOFIMA_CHECK_LAUNCH(ctx);
     }
     return SOFIMA_OK;

@@ -92,12 +92,20 @@ pack3_kernel(Problem3 P, const float* __restrict__ means, float2* __restrict__ Z
 // In-place complex FFT of `nlines` strided lines of length F.L:
 //   line l starts at (l / inner) * outer_stride + (l % inner) * inner_stride,
 //   consecutive elements are `es` apart.  C lines per block.
+// Lines of a pass are numbered (volume, a, b) with a < An, b < Bn; a pass that only needs the
+// lines with a < Au and b < Bu (forward passes over zero-padded volumes: every other line is
+// all zeros and stays all zeros) numbers exactly those.  An = Au = Bn = Bu = 1 means "all".
+struct LinePrune {
+  long long An, Au, Bn, Bu;
+};
+
 template <bool INV>
 __global__ void __launch_bounds__(kThreads)
 axis_fft_kernel(float2* __restrict__ data, long long nlines, long long inner,
                 long long inner_stride, long long outer_stride, long long es, FftPlan F,
-                int C) {
+                int C, LinePrune pr) {
   extern __shared__ float2 smem[];
+  __shared__ long long base_s[16];
   const int L = F.L;
   float2* w0 = smem;
   float2* w1 = w0 + (size_t)C * L;
@@ -105,19 +113,24 @@ axis_fft_kernel(float2* __restrict__ data, long long nlines, long long inner,
   load_twiddles(tw_s, F);
   const long long l0 = (long long)blockIdx.x * C;
   const int nc = (int)min((long long)C, nlines - l0);
-  auto line_base = [&](long long l) {
-    return (l / inner) * outer_stride + (l % inner) * inner_stride;
-  };
+  if ((int)threadIdx.x < nc) {  // one address computation per line, not per element
+    const long long lp = l0 + threadIdx.x;
+    const long long per = pr.Au * pr.Bu;
+    const long long v = lp / per, r = lp - v * per;
+    const long long a = r / pr.Bu, b = r - a * pr.Bu;
+    const long long l = (v * pr.An + a) * pr.Bn + b;
+    base_s[threadIdx.x] = (l / inner) * outer_stride + (l % inner) * inner_stride;
+  }
+  __syncthreads();
   if (es == 1) {
     for (int i = threadIdx.x; i < C * L; i += kThreads) {
       const int c = i / L, k = i - c * L;
-      w0[i] = c < nc ? data[line_base(l0 + c) + k] : make_float2(0.f, 0.f);
+      w0[i] = c < nc ? data[base_s[c] + k] : make_float2(0.f, 0.f);
     }
   } else {
     for (int i = threadIdx.x; i < C * L; i += kThreads) {
       const int k = i / C, c = i - k * C;  // c fastest: neighbouring lines are adjacent
-      w0[c * L + k] = c < nc ? data[line_base(l0 + c) + (long long)k * es]
-                             : make_float2(0.f, 0.f);
+      w0[c * L + k] = c < nc ? data[base_s[c] + (long long)k * es] : make_float2(0.f, 0.f);
     }
   }
   __syncthreads();
@@ -125,12 +138,12 @@ axis_fft_kernel(float2* __restrict__ data, long long nlines, long long inner,
   if (es == 1) {
     for (int i = threadIdx.x; i < C * L; i += kThreads) {
       const int c = i / L, k = i - c * L;
-      if (c < nc) data[line_base(l0 + c) + k] = res[i];
+      if (c < nc) data[base_s[c] + k] = res[i];
     }
   } else {
     for (int i = threadIdx.x; i < C * L; i += kThreads) {
       const int k = i / C, c = i - k * C;
-      if (c < nc) data[line_base(l0 + c) + (long long)k * es] = res[c * L + k];
+      if (c < nc) data[base_s[c] + (long long)k * es] = res[c * L + k];
     }
   }
 }

@@ -116,17 +116,24 @@ class StitchAndRender3dTiles(compat.SubvolumeProcessor):
 
   def _get_dts(self, shape, tx: int, ty: int) -> np.ndarray:
     """Blending weight of a tile: distance from its usable area's edge
-    (processor/warp.py:151-165).  `margin` pixels are ignored on inner edges only."""
-    mask = np.zeros(shape[1:], dtype=bool)
+    (processor/warp.py:151-165).  `margin` pixels are ignored on inner edges only.  The
+    usable area is a rectangle, so its Euclidean distance transform (everything outside the
+    array counts as background) is the distance to the nearest side -- computed directly;
+    `_border_distance` is the general form it is checked against."""
+    h, w = int(shape[1]), int(shape[2])
     if self._margin > 0:
       x0 = self._margin if tx > 0 else 0
       x1 = -self._margin if tx < self._tile_map.shape[-1] - 1 else -1
       y0 = self._margin if ty > 0 else 0
       y1 = -self._margin if ty < self._tile_map.shape[-2] - 1 else -1
-      mask[y0:y1, x0:x1] = 1
+      ys, xs = slice(y0, y1).indices(h), slice(x0, x1).indices(w)
+      y0, y1, x0, x1 = ys[0], ys[1], xs[0], xs[1]
     else:
-      mask[...] = 1
-    return _border_distance(mask)
+      y0, y1, x0, x1 = 0, h, 0, w
+    yy = np.arange(h, dtype=np.float32)[:, None]
+    xx = np.arange(w, dtype=np.float32)[None, :]
+    dist = np.minimum(np.minimum(yy - (y0 - 1), y1 - yy), np.minimum(xx - (x0 - 1), x1 - xx))
+    return np.maximum(dist, 0).astype(np.float32)
 
   def _dts_on_device(self, shape, tx: int, ty: int):
     """`_get_dts` of a tile, computed once per instance and kept on the device."""

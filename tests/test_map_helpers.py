@@ -117,3 +117,29 @@ def test_resample_map():
   resampled = map_utils.resample_map(coord_map, box, dst_box, 40, 20)
   np.testing.assert_array_almost_equal(resampled[:, :, :-1, :-1], expected[:, :, 6:-1, 4:-1],
                                        decimal=2)
+
+
+def test_tile_blending_weight_equals_distance_transform():
+  """StitchAndRender3dTiles._get_dts (analytic, rectangle) == the Euclidean distance
+  transform with a black border that the reference computes with `edt`
+  (processor/warp.py:151-165), for inner / outer tiles with and without a margin."""
+  from sofima_b200.processor import warp as pwarp
+  for margin in (0, 3, 7):
+    r = pwarp.StitchAndRender3dTiles(tile_map=[[1, 2, 3], [4, 5, 6], [7, 8, 9]],
+                                     tile_mesh_path=None, tile_pattern_path='', stride=(8, 8, 8),
+                                     margin=margin)
+    for tx in range(3):
+      for ty in range(3):
+        got = r._get_dts((4, 37, 45), tx, ty)
+        mask = np.zeros((37, 45), bool)
+        if margin > 0:
+          x0 = margin if tx > 0 else 0
+          x1 = -margin if tx < 2 else -1
+          y0 = margin if ty > 0 else 0
+          y1 = -margin if ty < 2 else -1
+          mask[y0:y1, x0:x1] = 1
+        else:
+          mask[...] = 1
+        want = pwarp._border_distance(mask)
+        assert got.dtype == np.float32
+        np.testing.assert_array_equal(got, want)
