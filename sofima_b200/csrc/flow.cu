@@ -66,11 +66,11 @@ __device__ __forceinline__ float2 twid(const float2* tw, int idx) {
   return w;
 }
 
-// One Stockham pass over `nfft` transforms stored as [nfft][L] in shared memory.
+// One Stockham pass over `nfft` transforms stored as [nfft][pitch] in shared memory.
 template <bool INV>
 __device__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ dst, int nfft,
-                         const FftPlan& P, int st, const float2* tw) {
-  const int r = P.radix[st], s = P.s[st], m = P.m[st], bf = P.bf[st], L = P.L;
+                         const FftPlan& P, int st, const float2* tw, int pitch) {
+  const int r = P.radix[st], s = P.s[st], m = P.m[st], bf = P.bf[st], L = pitch;
   const unsigned mgb = P.mg_bf[st], mgs = P.mg_s[st];
   const int total = nfft * bf;
   const int sm = s * m;
@@ -123,11 +123,15 @@ __device__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ ds
 }
 
 // Full transform of `nfft` lines; returns the buffer that holds the result.
+// `pitch`: float2 between consecutive lines (0 = P.L; an odd pitch keeps column-wise accesses
+// to the lines conflict-free).
 template <bool INV>
-__device__ float2* block_fft(float2* a, float2* b, int nfft, const FftPlan& P, const float2* tw) {
+__device__ float2* block_fft(float2* a, float2* b, int nfft, const FftPlan& P, const float2* tw,
+                             int pitch = 0) {
+  if (pitch == 0) pitch = P.L;
   float2 *src = a, *dst = b;
   for (int st = 0; st < P.nstages; ++st) {
-    fft_pass<INV>(src, dst, nfft, P, st, tw);
+    fft_pass<INV>(src, dst, nfft, P, st, tw, pitch);
     __syncthreads();
     float2* t = src; src = dst; dst = t;
   }
@@ -1522,7 +1526,8 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
   if (nsub > B) nsub = B;
   void *Z = nullptr, *means = nullptr;
   if ((rc = scratch(ctx, "flow3.Z", sizeof(float2) * 2 * nsub * vol, &Z))) return rc;
-  if ((rc = scratch(ctx, "flow3.means", sizeof(float) * 2 * B, &means))) return rc;
+  if ((rc = scratch(ctx, "flow3.mean_parts", sizeof(double) * 2 * B * kMeanSlices, &means)))
+    return rc;
   const size_t smem_cap = 200 * 1024;
   SOFIMA_CUDA(ctx, cudaFuncSetAttribute(axis_fft_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1532,7 +1537,7 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
                                         (int)smem_cap));
   auto lines_per_block = [&](int L) {
     int C = 16;
-    while (C > 1 && (size_t)(2 * C + 1) * L * sizeof(float2) > 96 * 1024) C /= 2;
+    while (C > 1 && ((size_t)2 * C * (L | 1) + L) * sizeof(float2) > 96 * 1024) C /= 2;
     return C;
   };
   const float scale = (float)(1.0 / ((double)P.Lx * P.Ly * P.Lz));
@@ -1543,10 +1548,11 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
     float2* Zp = static_cast<float2*>(Z);
     {
       LaunchTimer timer(ctx, "flow3_pack");
-      patch_mean3_kernel<<<dim3(nb, 2), kThreads, 0, ctx->stream>>>(P, (float*)means);
+      patch_mean3_kernel<<<dim3(nb, 2, kMeanSlices), kThreads, 0, ctx->stream>>>(
+          P, (double*)means);
       SOFIMA_CHECK_LAUNCH(ctx);
       pack3_kernel<<<dim3(ctx->num_sms * 2, 2, nb), kThreads, 0, ctx->stream>>>(
-          P, (const float*)means, Zp);
+          P, (const double*)means, Zp);
       SOFIMA_CHECK_LAUNCH(ctx);
     }
     // transforms over x, y, z of all 2 * nb volumes (forward), then of the nb products.
@@ -1575,7 +1581,7 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
       for (int a = 0; a < 3; ++a) {
         const Axis& A = axes[inverse ? 2 - a : a];
         const int C = lines_per_block(A.F->L);
-        const size_t smem = (size_t)(2 * C + 1) * A.F->L * sizeof(float2);
+        const size_t smem = ((size_t)2 * C * (A.F->L | 1) + A.F->L) * sizeof(float2);
         const unsigned grid = (unsigned)ceil_div<long long>(A.nlines, C);
         LaunchTimer timer(ctx, "flow3_fft");
         if (inverse)
@@ -1687,7 +1693,7 @@ static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, cons
                                         (int)smem_cap));
   auto lines_per_block = [&](int L) {
     int C = 16;
-    while (C > 1 && (size_t)(2 * C + 1) * L * sizeof(float2) > 96 * 1024) C /= 2;
+    while (C > 1 && ((size_t)2 * C * (L | 1) + L) * sizeof(float2) > 96 * 1024) C /= 2;
     return C;
   };
   // in-place transforms over x, y, z (forward) / z, y, x (inverse) of nvol volumes
@@ -1702,7 +1708,7 @@ static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, cons
     for (int a = 0; a < 3; ++a) {
       const Axis& A = axes[inverse ? 2 - a : a];
       const int C = lines_per_block(A.F->L);
-      const size_t smem = (size_t)(2 * C + 1) * A.F->L * sizeof(float2);
+      const size_t smem = ((size_t)2 * C * (A.F->L | 1) + A.F->L) * sizeof(float2);
       const unsigned grid = (unsigned)ceil_div<long long>(A.nlines, C);
       LaunchTimer timer(ctx, "flow3_fft");
       if (inverse)
