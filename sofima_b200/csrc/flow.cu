@@ -1481,6 +1481,54 @@ static int run_fused(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* 
 
 namespace sofima {
 namespace flow {
+// Register-codelet axis pass (flow3d.cuh) for L = 16 * N2; false if the length has none.
+template <int N2>
+static bool launch_axis_fast_n2(sofima_ctx* ctx, bool inverse, float2* data, long long nlines,
+                                long long inner, long long istride, long long ostride,
+                                long long es, const float2* tw, const LinePrune& pr) {
+  using D = AxisFast<N2>;
+  static bool configured[2] = {false, false};
+  if (!configured[inverse]) {
+    const cudaError_t e = inverse
+        ? cudaFuncSetAttribute(axis_fft_fast_kernel<N2, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::smem)
+        : cudaFuncSetAttribute(axis_fft_fast_kernel<N2, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::smem);
+    if (e != cudaSuccess) return false;
+    configured[inverse] = true;
+  }
+  const unsigned grid = (unsigned)ceil_div<long long>(nlines, D::C);
+  if (inverse)
+    axis_fft_fast_kernel<N2, true><<<grid, D::NT, D::smem, ctx->stream>>>(
+        data, nlines, inner, istride, ostride, es, tw, pr);
+  else
+    axis_fft_fast_kernel<N2, false><<<grid, D::NT, D::smem, ctx->stream>>>(
+        data, nlines, inner, istride, ostride, es, tw, pr);
+  return true;
+}
+
+static bool launch_axis_fast(sofima_ctx* ctx, int L, bool inverse, float2* data, long long nlines,
+                             long long inner, long long istride, long long ostride, long long es,
+                             const float2* tw, const LinePrune& pr) {
+  if (const char* e = getenv("SOFIMA_FLOW3D_FAST"))
+    if (e[0] == '0') return false;
+  int n2 = 0;
+  if (!fast_n2(L, &n2)) return false;
+  switch (n2) {
+    case 8: return launch_axis_fast_n2<8>(ctx, inverse, data, nlines, inner, istride, ostride, es, tw, pr);
+    case 10: return launch_axis_fast_n2<10>(ctx, inverse, data, nlines, inner, istride, ostride, es, tw, pr);
+    case 12: return launch_axis_fast_n2<12>(ctx, inverse, data, nlines, inner, istride, ostride, es, tw, pr);
+    case 15: return launch_axis_fast_n2<15>(ctx, inverse, data, nlines, inner, istride, ostride, es, tw, pr);
+    case 16: return launch_axis_fast_n2<16>(ctx, inverse, data, nlines, inner, istride, ostride, es, tw, pr);
+    case 20: return launch_axis_fast_n2<20>(ctx, inverse, data, nlines, inner, istride, ostride, es, tw, pr);
+    default: return false;
+  }
+}
+}  // namespace flow
+}  // namespace sofima
+
+namespace sofima {
+namespace flow {
 
 static int run_xcorr3_masked(sofima_ctx* ctx, const sofima_xcorr_params* p, const void* pre_img,
                              const void* post_img, const uint8_t* pre_mask,
@@ -1584,6 +1632,11 @@ static int run_xcorr3(sofima_ctx* ctx, const sofima_xcorr_params* p, const void*
         const size_t smem = ((size_t)2 * C * (A.F->L | 1) + A.F->L) * sizeof(float2);
         const unsigned grid = (unsigned)ceil_div<long long>(A.nlines, C);
         LaunchTimer timer(ctx, "flow3_fft");
+        if (launch_axis_fast(ctx, A.F->L, inverse, Zp, A.nlines, A.inner, A.istride, A.ostride,
+                             A.es, A.F->tw, A.pr)) {
+          SOFIMA_CHECK_LAUNCH(ctx);
+          continue;
+        }
         if (inverse)
           axis_fft_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(
               Zp, A.nlines, A.inner, A.istride, A.ostride, A.es, *A.F, C, A.pr);

@@ -161,6 +161,99 @@ axis_fft_kernel(float2* __restrict__ data, long long nlines, long long inner,
   }
 }
 
+// The same pass for lengths L = 16 * N2 with all butterflies in registers (the codelets of the
+// 2-d fast path): thread (line c, r) runs a 16-point DFT over the elements N2 n1 + r, the
+// results are twiddled and exchanged through shared memory, thread (c, k1) runs the N2-point
+// DFT and owns the bins k1 + 16 k2.  16 neighbouring lines per block (c fastest: strided
+// passes read and write 128-byte runs); contiguous lines (es == 1) are staged through shared
+// memory so that their global accesses are coalesced too.  The inverse is the forward
+// transform with real and imaginary parts swapped on the way in and out.
+template <int N2>
+struct AxisFast {
+  static constexpr int L = kN1 * N2;
+  static constexpr int C = 16;
+  static constexpr int G = N2 > kN1 ? N2 : kN1;
+  static constexpr int NT = C * G;
+  static constexpr int N2P = N2 | 1;
+  static constexpr int EX = kN1 * N2P + 1;  // odd: the 16 lines fall on 16 different banks
+  static constexpr int XP = L + 1;
+  static constexpr size_t smem = sizeof(float2) * ((size_t)C * EX + (size_t)C * XP + L);
+};
+
+template <int N2, bool INV>
+__global__ void __launch_bounds__(AxisFast<N2>::NT)
+axis_fft_fast_kernel(float2* __restrict__ data, long long nlines, long long inner,
+                     long long inner_stride, long long outer_stride, long long es,
+                     const float2* __restrict__ tw, LinePrune pr) {
+  using D = AxisFast<N2>;
+  constexpr int L = D::L, C = D::C;
+  extern __shared__ float2 smem[];
+  __shared__ long long base_s[C];
+  float2* ex = smem;
+  float2* xs = ex + C * D::EX;
+  float2* tw_s = xs + C * D::XP;
+  stage_twiddles<L, D::NT>(tw_s, tw);
+  const long long l0 = (long long)blockIdx.x * C;
+  const int nc = (int)min((long long)C, nlines - l0);
+  if ((int)threadIdx.x < nc) {
+    const long long lp = l0 + threadIdx.x;
+    const long long per = pr.Au * pr.Bu;
+    const long long v = lp / per, rr = lp - v * per;
+    const long long a = rr / pr.Bu, b = rr - a * pr.Bu;
+    const long long l = (v * pr.An + a) * pr.Bn + b;
+    base_s[threadIdx.x] = (l / inner) * outer_stride + (l % inner) * inner_stride;
+  }
+  __syncthreads();
+  const int c = threadIdx.x % C, r = threadIdx.x / C;
+  const bool contiguous = es == 1;
+  if (contiguous) {
+    for (int i = threadIdx.x; i < C * L; i += D::NT) {
+      const int cc = i / L, k = i - cc * L;
+      xs[cc * D::XP + k] = cc < nc ? data[base_s[cc] + k] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+  }
+  float2 a[kN1];
+  if (r < N2) {
+#pragma unroll
+    for (int n1 = 0; n1 < kN1; ++n1) {
+      const int k = N2 * n1 + r;
+      float2 v;
+      if (contiguous) v = xs[c * D::XP + k];
+      else v = c < nc ? data[base_s[c] + (long long)k * es] : make_float2(0.f, 0.f);
+      a[n1] = INV ? swap_ri(v) : v;
+    }
+    Dft<kN1>::run(a);
+  }
+  stage_twiddles_wait();
+  __syncthreads();  // twiddles staged
+  if (r < N2) {
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; ++k1) ex[c * D::EX + k1 * D::N2P + r] = cmul(a[k1], tw_s[r * k1]);
+  }
+  __syncthreads();
+  if (r < kN1) {
+    float2 bq[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) bq[n2] = ex[c * D::EX + r * D::N2P + n2];
+    Dft<N2>::run(bq);
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) {
+      const int k = r + kN1 * k2;
+      const float2 v = INV ? swap_ri(bq[k2]) : bq[k2];
+      if (contiguous) xs[c * D::XP + k] = v;
+      else if (c < nc) data[base_s[c] + (long long)k * es] = v;
+    }
+  }
+  if (contiguous) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * L; i += D::NT) {
+      const int cc = i / L, k = i - cc * L;
+      if (cc < nc) data[base_s[cc] + k] = xs[cc * D::XP + k];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 multiply3_kernel(float2* __restrict__ a, const float2* __restrict__ b, long long n) {
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
