@@ -635,9 +635,13 @@ peak1_kernel(const float* __restrict__ img, PeakParams pp, unsigned long long* k
   __syncthreads();
   const long long n = (long long)pp.sz * pp.sy * pp.sx;
   const float* im = img + blockIdx.x * n;
+  // gridDim.y blocks share one image (3-d correlation volumes have millions of voxels); the
+  // keys are ordered by (value, lowest index), so atomicMax gives the same result as one block.
+  // keys / nanflag are zeroed by the caller.
+  const long long i0 = n * blockIdx.y / gridDim.y, i1 = n * (blockIdx.y + 1) / gridDim.y;
   unsigned long long best = 0;
   int has_nan = 0;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+  for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
     const float v = im[i];
     if (v != v) has_nan = 1;
     const unsigned long long k = peak_key(v, (unsigned)i);
@@ -646,8 +650,8 @@ peak1_kernel(const float* __restrict__ img, PeakParams pp, unsigned long long* k
   if (has_nan) nan_flag = 1;
   best = block_max_key(best, sm);
   if (threadIdx.x == 0) {
-    keys[blockIdx.x] = best;
-    nanflag[blockIdx.x] = nan_flag;
+    if (best != 0) atomicMax(&keys[blockIdx.x], best);
+    if (nan_flag) atomicOr(&nanflag[blockIdx.x], 1);
   }
 }
 
@@ -689,10 +693,39 @@ __device__ __forceinline__ bool is_peak(const float* im, const PeakParams& pp, i
 }
 
 // Pass 2: second peak under the batch-coupled exclusion rule + statistics.
+// Second-peak candidates of large (3-d) correlation volumes: gridDim.y blocks share one image
+// and combine their best (value, lowest index) key with atomicMax -- the same result as the
+// scan inside peak2_kernel, which then only reads the key.  keys2 is zeroed by the caller.
+__global__ void __launch_bounds__(kThreads)
+peak2_scan_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a,
+                  const unsigned* __restrict__ bitmap, unsigned long long* keys2) {
+  __shared__ unsigned long long sm[kThreads / 32];
+  const long long n = (long long)pp.sz * pp.sy * pp.sx;
+  const float* im = img + blockIdx.x * n;
+  const float v1 = v1a[blockIdx.x];
+  if (v1 == -INFINITY) return;
+  const float thr = pp.thr_rel * v1;
+  const long long i0 = n * blockIdx.y / gridDim.y, i1 = n * (blockIdx.y + 1) / gridDim.y;
+  unsigned long long best = 0;
+  for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
+    const float v = __ldg(im + i);
+    if (!(v > thr)) continue;
+    if ((bitmap[i >> 5] >> (i & 31)) & 1u) continue;  // erased for every row (:263-265)
+    const int x = (int)(i % pp.sx), r = (int)(i / pp.sx);
+    const int y = r % pp.sy, z = r / pp.sy;
+    if (!is_peak(im, pp, z, y, x, v)) continue;
+    const unsigned long long k = peak_key(v, (unsigned)i);
+    best = k > best ? k : best;
+  }
+  best = block_max_key(best, sm);
+  if (threadIdx.x == 0 && best != 0) atomicMax(&keys2[blockIdx.x], best);
+}
+
 __global__ void __launch_bounds__(kThreads)
 peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, const int* p1a,
              const unsigned* __restrict__ bitmap, int ndim_out, float* out,
-             const float* __restrict__ bandmax, int band_rows, int nbands) {
+             const float* __restrict__ bandmax, int band_rows, int nbands,
+             const unsigned long long* __restrict__ keys2) {
   __shared__ unsigned long long sm[kThreads / 32];
   __shared__ float smin[kThreads / 32];
   const long long n = (long long)pp.sz * pp.sy * pp.sx;
@@ -727,7 +760,9 @@ peak2_kernel(const float* __restrict__ img, PeakParams pp, const float* v1a, con
     }
     for (; i < hi; i += kThreads) consider(i, __ldg(im + i));
   };
-  if (bandmax != nullptr) {
+  if (keys2 != nullptr) {
+    best = keys2[blockIdx.x];  // found by peak2_scan_kernel
+  } else if (bandmax != nullptr) {
     // rows_inv_fast recorded the maximum of every band of `band_rows` rows: bands
     // that cannot hold a pixel above the threshold are never read.
     const float* bmx = bandmax + (long long)blockIdx.x * nbands;
@@ -865,9 +900,12 @@ static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const Pe
   SOFIMA_CUDA(ctx, cudaMemsetAsync(bm, 0, sizeof(unsigned) * words, ctx->stream));
   if (!keys_ready) {
     LaunchTimer timer(ctx, "flow_peak1");
-    peak1_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp,
-                                                            (unsigned long long*)keys,
-                                                            (int*)nanf);
+    SOFIMA_CUDA(ctx, cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * B, ctx->stream));
+    SOFIMA_CUDA(ctx, cudaMemsetAsync(nanf, 0, sizeof(int) * B, ctx->stream));
+    long long slices = n / 65536;
+    slices = slices < 1 ? 1 : (slices > 64 ? 64 : slices);
+    peak1_kernel<<<dim3((unsigned)B, (unsigned)slices), kThreads, 0, ctx->stream>>>(
+        images, pp, (unsigned long long*)keys, (int*)nanf);
     SOFIMA_CHECK_LAUNCH(ctx);
   }
   peak1_decode_kernel<<<(unsigned)ceil_div<long long>(B, 256), 256, 0, ctx->stream>>>(
@@ -882,10 +920,22 @@ static int run_peaks(sofima_ctx* ctx, const float* images, long long B, const Pe
       if ((rc = scratch(ctx, "flow.bandmax", sizeof(float) * B * nbands, &bmx))) return rc;
       bandmax = static_cast<const float*>(bmx);
     }
+    const unsigned long long* keys2 = nullptr;
+    if (n >= (1ll << 20) && bandmax == nullptr) {  // 3-d volumes: spread the scan over the GPU
+      void* k2 = nullptr;
+      if ((rc = scratch(ctx, "flow.keys2", sizeof(unsigned long long) * B, &k2))) return rc;
+      SOFIMA_CUDA(ctx, cudaMemsetAsync(k2, 0, sizeof(unsigned long long) * B, ctx->stream));
+      long long slices = n / 65536;
+      slices = slices > 64 ? 64 : slices;
+      peak2_scan_kernel<<<dim3((unsigned)B, (unsigned)slices), kThreads, 0, ctx->stream>>>(
+          images, pp, (const float*)v1, (const unsigned*)bm, (unsigned long long*)k2);
+      SOFIMA_CHECK_LAUNCH(ctx);
+      keys2 = static_cast<const unsigned long long*>(k2);
+    }
     peak2_kernel<<<(unsigned)B, kThreads, 0, ctx->stream>>>(images, pp, (const float*)v1,
                                                             (const int*)p1, (const unsigned*)bm,
                                                             pp.ndim + 2, out_peaks, bandmax,
-                                                            band_rows, nbands);
+                                                            band_rows, nbands, keys2);
     SOFIMA_CHECK_LAUNCH(ctx);
   }
   return SOFIMA_OK;
