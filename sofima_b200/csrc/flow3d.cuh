@@ -1,10 +1,11 @@
 // 3-d patch correlation (reference flow_field.py:36-89 with dim = 3, unmasked).
 //
-// Correctness-first: every patch is packed into a zero-padded complex volume
-// [Lz][Ly][Lx], transformed along x, y, z with the generic shared-memory Stockham
-// FFT (strided lines), multiplied, transformed back and cropped.  The peak kernels
-// of flow.cu are dimension-generic.  (The 2-d kernels are the tuned path; 3-d
-// volumes appear in BASELINE config 5 only.)
+// Every patch is packed into a zero-padded complex volume [Lz][Ly][Lx], transformed along
+// x, y, z (forward passes skip the all-zero lines), multiplied, transformed back and
+// cropped.  Lengths of the form 16 * N2 use the register codelets of the 2-d fast path
+// (axis_fft_fast_kernel: 16 neighbouring lines per block, coalesced strided passes); other
+// 5-smooth lengths the generic shared-memory Stockham pass (axis_fft_kernel).  The peak
+// kernels of flow.cu are dimension-generic.  BASELINE config 5.
 #pragma once
 
 namespace sofima {
