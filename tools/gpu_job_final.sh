@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-end style visit: parity tests, smoke, the default bench line, the reference arm,
-# ncu launch list + full captures (never a bench number), warp path, config 5 with rendering
+# ncu launch list (never a bench number), warp path
 mkdir -p gpurun_out
 ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log
@@ -8,12 +8,8 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -2 gpurun_out/bench.err
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-timeout 100 python tools/e2e_breakdown.py > gpurun_out/e2e_breakdown.json 2> gpurun_out/e2e_breakdown.err
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --mesh-iters 50 --no-cpu-baseline > gpurun_out/b_under_ncu.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'cols_fast|rows_inv_fast|rowspec_tc' -s 6 -c 3 -f -o gpurun_out/prof_flow_final python tools/prof_target.py flow > gpurun_out/ncu_flow_final.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'mesh2d_kernel' -s 10 -c 1 -f -o gpurun_out/prof_mesh_final python tools/prof_target.py mesh > gpurun_out/ncu_mesh_final.log 2>&1
 for m in lanczos linear nearest; do
   timeout 300 python tools/bench_warp.py --interpolation $m --out gpurun_out/warp_r2_$m.json > /dev/null 2> gpurun_out/warp_$m.err
 done
-timeout 900 python tools/config_runs.py config5 --depth 128 --render > gpurun_out/config5_r2_render.json 2> gpurun_out/config5_r2_render.err
 cut -c1-300 gpurun_out/bench.json
