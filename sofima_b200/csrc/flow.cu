@@ -1537,15 +1537,16 @@ static bool launch_axis_fast_n2(sofima_ctx* ctx, bool inverse, float2* data, lon
                                 long long inner, long long istride, long long ostride,
                                 long long es, const float2* tw, const LinePrune& pr) {
   using D = AxisFast<N2>;
-  static bool configured[2] = {false, false};
-  if (!configured[inverse]) {
+  if (D::smem > 48 * 1024) {  // opt-in is per device: set it on every call (cheap)
     const cudaError_t e = inverse
         ? cudaFuncSetAttribute(axis_fft_fast_kernel<N2, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::smem)
         : cudaFuncSetAttribute(axis_fft_fast_kernel<N2, false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::smem);
-    if (e != cudaSuccess) return false;
-    configured[inverse] = true;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return false;  // the generic pass takes over
+    }
   }
   const unsigned grid = (unsigned)ceil_div<long long>(nlines, D::C);
   if (inverse)
