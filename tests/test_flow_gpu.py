@@ -452,3 +452,28 @@ def test_fused_pipeline_second_peak_rule(ff, monkeypatch):
   fused = calc.flow_field(pre, post, **kw)
   np.testing.assert_array_equal(fused, three)
   assert (three[3][np.isfinite(three[3])] > 0).any()            # second peaks do exist
+
+
+def test_3d_register_codelet_axis_passes(ff, monkeypatch):
+  """3-d patches whose padded lengths are 16 * N2 (64 -> 128, 80 -> 160, 96 -> 192: N2 = 8, 10,
+  12 in one call) go through axis_fft_fast_kernel with pruned forward passes; the generic
+  Stockham passes (SOFIMA_FLOW3D_FAST=0) and the oracle must give the same integer flow."""
+  rng = np.random.default_rng(11)
+  base = ndi.gaussian_filter(rng.standard_normal((110, 130, 150)), 1.5)
+  base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+  pre = np.ascontiguousarray(base[4:100, 6:118, 8:136])
+  post = np.ascontiguousarray(base[6:102, 3:115, 12:140])
+  kw = dict(patch_size=(64, 80, 96), step=(32, 32, 32), batch_size=4)
+  calc = ff.JAXMaskedXCorrWithStatsCalculator(peak_radius=(3, 3, 3))
+  fast = calc.flow_field(pre, post, **kw)
+  monkeypatch.setenv('SOFIMA_FLOW3D_FAST', '0')
+  generic = calc.flow_field(pre, post, **kw)
+  monkeypatch.delenv('SOFIMA_FLOW3D_FAST')
+  assert fast.shape == generic.shape and fast.shape[0] == 5
+  np.testing.assert_array_equal(fast[:3], generic[:3])
+  np.testing.assert_allclose(fast[3:], generic[3:], rtol=2e-3, atol=1e-5)
+  assert np.isfinite(fast[:3]).all()
+  # pre = base[4:, 6:, 8:], post = base[6:, 3:, 12:]: one shift for every patch (x, y, z)
+  assert (fast[0] == 4).all() and (fast[1] == -3).all() and (fast[2] == 2).all()
+  want = fo.MaskedXCorrWithStatsCalculator(peak_radius=(3, 3, 3)).flow_field(pre, post, **kw)
+  _check_flow(fast, want)

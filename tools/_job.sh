@@ -1,2 +1,1 @@
-timeout 850 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 tools/config_runs.py config5 --depth 128 --render --problems 32 > gpurun_out/config5_r2_n8.json 2> gpurun_out/config5_r2_n8.err
-grep '^{' gpurun_out/config5_r2_n8.json | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('flow_seconds','mesh_seconds','render_seconds','problem_seconds','job_seconds','per_problem_seconds_rank0')})"
+timeout 600 python -m pytest tests/test_flow_gpu.py -x -q -m gpu -k "3d" 2>&1 | tail -8
