@@ -6,6 +6,9 @@
   fill_missing             map_utils.py:227-304   (host, SciPy qhull like the reference)
   invert_map               map_utils.py:392-487   (host, SciPy qhull like the reference)
   resample_map             map_utils.py:490-546   (host, SciPy qhull like the reference)
+  compose_maps             map_utils.py:549-613   (host, the slow scattered form; the per-node
+                                                   gather is compose_maps_fast on the GPU)
+  make_affine_map          map_utils.py:789-811   (host bookkeeping)
 
 The scattered-data steps (Delaunay triangulation + piecewise-linear / nearest lookup) work
 on the coarse map nodes -- thousands of points, not pixels -- and are scipy.spatial /
@@ -272,6 +275,47 @@ def resample_map(coord_map: np.ndarray, src_box, dst_box, src_stride: float,
     out[0, z, ...] = u.reshape(tx.shape)
     out[1, z, ...] = v.reshape(ty.shape)
   return out
+
+
+def compose_maps(map1: np.ndarray, box1, stride1: float, map2: np.ndarray, box2,
+                 stride2: float) -> np.ndarray:
+  """map2(map1(x, y)) for [2, z, y, x] relative maps by scattered-data interpolation
+  (map_utils.py:549-613): map2's valid nodes are the data points, map1's absolute targets
+  the queries; invalid nodes of map2 are thereby interpolated over."""
+  assert map1.shape[0] == 2
+  assert map2.shape[0] == 2
+  abs1 = to_absolute(map1, stride1, box1)
+  abs2 = to_absolute(map2, stride2, box2)
+  out = np.full_like(map1, np.nan)
+  sy, sx = np.mgrid[box2.start[1]:box2.end[1], box2.start[0]:box2.end[0]]
+  sx = sx * stride2
+  sy = sy * stride2
+  for z in range(map1.shape[1]):
+    ok1 = np.all(np.isfinite(abs1[:, z, ...]), axis=0)
+    ok2 = np.all(np.isfinite(abs2[:, z, ...]), axis=0)
+    if not np.any(ok1) or not np.any(ok2):
+      continue
+    try:
+      u, v = _interpolate_points((sx[ok2], sy[ok2]),
+                                 (abs1[0, z, ...][ok1], abs1[1, z, ...][ok1]),
+                                 abs2[0, z, ...][ok2], abs2[1, z, ...][ok2])
+    except _QhullError:
+      continue
+    out[0, z, ...][ok1] = u
+    out[1, z, ...][ok1] = v
+  return to_relative(out, stride1, box1)
+
+
+def make_affine_map(matrix: np.ndarray, box, stride) -> np.ndarray:
+  """Relative [3, z, y, x] map of an affine transform (map_utils.py:789-811); `matrix` is
+  [3, 4] in the format of ndimage.affine_transform, acting on (x, y, z)."""
+  zyx = _identity_offsets(tuple(int(v) for v in box.size[::-1]), stride)
+  coords = np.array(zyx[::-1], dtype=np.float64)  # x, y, z
+  for i in range(3):
+    coords[i, ...] += box.start[i]
+  moved = (np.dot(matrix[:3, :3], coords.reshape((3, -1)))
+           + matrix[:, 3][:, np.newaxis]).reshape(coords.shape)
+  return moved - coords
 
 
 def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,

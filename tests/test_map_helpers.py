@@ -143,3 +143,32 @@ def test_tile_blending_weight_equals_distance_transform():
         want = pwarp._border_distance(mask)
         assert got.dtype == np.float32
         np.testing.assert_array_equal(got, want)
+
+
+def test_compose_maps():
+  """tests/map_utils_test.py:248-264: a map composed with its inverse is the identity."""
+  box = compat.BoundingBox(start=(100, 200, 10), size=(50, 50, 1))
+  coord_map = np.zeros([2, 1, 50, 50])
+  hy, hx = np.mgrid[:50, :50]
+  coord_map[0, 0, ...] = np.sin(hx / 25)
+  coord_map[1, 0, ...] = np.cos(hy / 25)
+  inverted = map_utils.invert_map(coord_map, box, box, 5)
+  composed = map_utils.compose_maps(coord_map, box, 5, inverted, box, 5)[:, :, 1:-2, 1:-2]
+  np.testing.assert_array_almost_equal(composed, np.zeros_like(composed), decimal=3)
+
+
+def test_make_affine_map():
+  box = compat.BoundingBox(start=(10, 20, 3), size=(6, 5, 4))
+  ident = np.hstack([np.eye(3), np.zeros((3, 1))])
+  np.testing.assert_array_equal(map_utils.make_affine_map(ident, box, (1, 2, 2)),
+                                np.zeros((3, 4, 5, 6)))
+  shift = ident.copy()
+  shift[:, 3] = (1.5, -2.0, 0.25)
+  m = map_utils.make_affine_map(shift, box, (1, 2, 2))
+  np.testing.assert_allclose(m[0], 1.5)
+  np.testing.assert_allclose(m[1], -2.0)
+  np.testing.assert_allclose(m[2], 0.25)
+  scale = ident.copy()
+  scale[0, 0] = 2.0  # x' = 2 x: relative x offset = absolute x position of the node
+  m = map_utils.make_affine_map(scale, box, (1, 2, 2))
+  np.testing.assert_allclose(m[0, 0, 0], (np.arange(6) * 2 + 10).astype(float))
