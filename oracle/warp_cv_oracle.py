@@ -314,3 +314,42 @@ def reference_pipeline(image, coord_map, stride, interpolation='lanczos', thread
   with futures.ThreadPoolExecutor(max_workers=threads) as ex:
     list(ex.map(section, range(nz)))
   return out
+
+
+class _Box:
+  """Minimal stand-in for a bounding box (xyz start / size) in the known-answer tests."""
+
+  def __init__(self, start, size):
+    self.start, self.size = np.asarray(start), np.asarray(size)
+    self.end = self.start + self.size
+
+
+def check_reference_kats(warp_subvolume_fn, box=_Box):
+  """The reference's own warp_subvolume tests (tests/warp_test.py:27-78) against any
+  implementation: label translation with ids beyond int32, and a 45-degree rotation of a
+  rhombus with the default (Lanczos) interpolation."""
+  image = np.zeros((1, 2, 100, 100), dtype=np.uint64)
+  image[0, 0, 40, 30] = 42
+  image[0, 1, 50, 40] = 2**40
+  cmap = np.zeros((2, 2, 15, 15))
+  cmap[0, 0] = 10
+  cmap[1, 1] = 17
+  warped = warp_subvolume_fn(image, box(start=(0, 0, 0), size=(100, 100, 2)), cmap,
+                             box(start=(0, 0, 0), size=(15, 15, 2)), 10,
+                             box(start=(10, 20, 0), size=(90, 80, 2)))
+  expected = np.zeros((1, 2, 80, 90))
+  expected[0, 0, 20, 10] = 42
+  expected[0, 1, 13, 30] = 2**40
+  np.testing.assert_array_equal(warped, expected)
+  hy, hx = np.mgrid[-50:50, -50:50]
+  img = np.zeros((1, 1, 100, 100), dtype=np.uint8)
+  img[0, 0][np.abs(hy) + np.abs(hx) < 25] = 255
+  ang = np.pi / 4
+  rmap = np.zeros((2, 1, 10, 10))
+  rmap[0, 0] = (np.cos(ang) * hx[::10, ::10] - np.sin(ang) * hy[::10, ::10]) - hx[::10, ::10]
+  rmap[1, 0] = (np.sin(ang) * hx[::10, ::10] + np.cos(ang) * hy[::10, ::10]) - hy[::10, ::10]
+  full = box(start=(0, 0, 0), size=(100, 100, 1))
+  warped = warp_subvolume_fn(img, full, rmap, box(start=(0, 0, 0), size=(10, 10, 1)), 10, full)
+  mask = np.zeros((1, 1, 100, 100), dtype=bool)
+  mask[0, 0, 33:68, 33:68] = True
+  assert np.all(warped[mask] > 128) and np.all(warped[~mask] < 64)

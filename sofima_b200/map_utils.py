@@ -9,6 +9,7 @@
   compose_maps             map_utils.py:549-613   (host, the slow scattered form; the per-node
                                                    gather is compose_maps_fast on the GPU)
   make_affine_map          map_utils.py:789-811   (host bookkeeping)
+  mask_irregular           map_utils.py:737-786   (CUDA tensors: csrc/flowfilt.cu; NumPy: as upstream)
 
 The scattered-data steps (Delaunay triangulation + piecewise-linear / nearest lookup) work
 on the coarse map nodes -- thousands of points, not pixels -- and are scipy.spatial /
@@ -30,6 +31,7 @@ from typing import Sequence
 
 import numpy as np
 from scipy import interpolate as _interpolate
+from scipy import ndimage
 from scipy import spatial as _spatial
 
 from . import _native
@@ -316,6 +318,48 @@ def make_affine_map(matrix: np.ndarray, box, stride) -> np.ndarray:
   moved = (np.dot(matrix[:3, :3], coords.reshape((3, -1)))
            + matrix[:, 3][:, np.newaxis]).reshape(coords.shape)
   return moved - coords
+
+
+def mask_irregular(coord_map: np.ndarray, stride: Sequence[float], frac: float,
+                   max_frac: float | None = None, dilation_iters: int = 1) -> np.ndarray:
+  """Marks stretched / folded nodes of a [2, y, x] relative map (map_utils.py:737-786).
+
+  A node is bad if the distance to its +x or +y neighbour is below `frac` or above
+  `max_frac` (default 2 - frac) times the stride; the bad set is dilated with a full
+  3x3 structuring element.  Bad nodes are set to NaN in place; returns the mask.
+  """
+  assert coord_map.ndim == 3 and coord_map.shape[0] == 2
+  if type(coord_map).__module__.startswith('torch') and coord_map.is_cuda:
+    # device-resident map: csrc/flowfilt.cu (same result, the mesh never leaves the GPU)
+    import ctypes
+    import torch
+    if coord_map.dtype != torch.float32 or not coord_map.is_contiguous():
+      raise ValueError('device mask_irregular needs a contiguous float32 [2, y, x] tensor')
+    ctx = _native.Context.get(coord_map.device.index)
+    ctx.bind_stream()
+    bad = torch.empty(coord_map.shape[1:], dtype=torch.uint8, device=coord_map.device)
+    rc = _native.lib().sofima_mask_irregular(
+        ctx.handle, coord_map.data_ptr(), int(coord_map.shape[1]), int(coord_map.shape[2]),
+        (ctypes.c_double * 2)(float(stride[0]), float(stride[1])), float(frac),
+        float(2 - frac if max_frac is None else max_frac), int(dilation_iters), bad.data_ptr())
+    _native.check(ctx.handle, rc)
+    return bad.bool()
+  # as upstream: the stride (a NumPy scalar of the `stride` array) promotes the fp32
+  # differences to float64 before the comparisons
+  stride = np.asarray(stride)
+  stride_x, stride_y = stride
+  hi = 2 - frac if max_frac is None else max_frac
+  diff_x = np.pad(np.diff(coord_map[0], axis=-1), [[0, 0], [0, 1]], mode='constant') + stride_x
+  diff_y = np.pad(np.diff(coord_map[1], axis=-2), [[0, 1], [0, 0]], mode='constant') + stride_y
+  with np.errstate(invalid='ignore'):
+    bad = (diff_x < frac * stride_x) | (diff_y < frac * stride_y)
+    bad |= (diff_x > hi * stride_x) | (diff_y > hi * stride_y)
+  if dilation_iters > 0:
+    bad = ndimage.binary_dilation(bad, ndimage.generate_binary_structure(2, 2),
+                                  iterations=dilation_iters)
+  coord_map[0][bad] = np.nan
+  coord_map[1][bad] = np.nan
+  return bad
 
 
 def compose_maps_fast(map1, start1: Sequence[float], stride1, map2,

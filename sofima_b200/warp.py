@@ -445,3 +445,37 @@ def render_tiles(tiles, coord_maps, stride=(20, 20), margin: int = 50, paralleli
   if return_warped_tiles:
     return canvas, covered, warped_tiles
   return canvas, covered
+
+
+def warp_points(points: np.ndarray, coord_map: np.ndarray, map_box, stride: float) -> np.ndarray:
+  """Maps [n, 3] xyz points through an in-plane [2, z, y, x] coordinate map
+  (warp.py:541-605).  Host bookkeeping on a handful of points: the map of every section that
+  holds a point is interpolated linearly (extrapolating) at the points, as upstream; integer
+  point arrays get rounded coordinates, z is unchanged."""
+  import collections  # pylint: disable=g-import-not-at-top
+  from scipy import interpolate  # pylint: disable=g-import-not-at-top
+  from . import map_utils  # pylint: disable=g-import-not-at-top
+  abs_map = map_utils.to_absolute(coord_map, stride)
+  abs_map += np.array(map_box.start[:2] * stride).reshape((2, 1, 1, 1))
+  by_z = collections.defaultdict(list)
+  for i, pt in enumerate(points):
+    by_z[pt[2]].append(i)
+  points = np.array(points)
+  assert points.ndim == 2 and points.shape[1] == 3
+  assert coord_map.shape[0] == 2
+  out = points.copy()
+  node_y = (np.arange(coord_map.shape[2]) + map_box.start[1]) * stride
+  node_x = (np.arange(coord_map.shape[3]) + map_box.start[0]) * stride
+  for z, idx in by_z.items():
+    z_rel = int(z - map_box.start[2])
+    query = points[idx, 1], points[idx, 0]  # yx
+    new = []
+    for comp in (0, 1):
+      dense = interpolate.RegularGridInterpolator((node_y, node_x), abs_map[comp, z_rel, ...],
+                                                  bounds_error=False, fill_value=None)
+      val = dense(query).astype(np.float32)
+      if np.issubdtype(out.dtype, np.integer):
+        val = np.round(val).astype(out.dtype)
+      new.append(val)
+    out[idx, 0], out[idx, 1] = new
+  return out

@@ -172,3 +172,28 @@ def test_make_affine_map():
   scale[0, 0] = 2.0  # x' = 2 x: relative x offset = absolute x position of the node
   m = map_utils.make_affine_map(scale, box, (1, 2, 2))
   np.testing.assert_allclose(m[0, 0, 0], (np.arange(6) * 2 + 10).astype(float))
+
+
+def test_warp_points():
+  """tests/warp_test.py:115-126."""
+  from sofima_b200 import warp
+  coord_map = np.zeros((2, 10, 3, 3))
+  coord_map[0, 0, ...] = 10
+  coord_map[1, 1, ...] = 20
+  points = np.array([[101, 201, 0], [105, 205, 1]])
+  map_box = compat.BoundingBox(start=(10, 20, 0), size=(3, 3, 10))
+  warped = warp.warp_points(points, coord_map, map_box, 10)
+  np.testing.assert_array_equal(warped, np.array([[111, 201, 0], [105, 225, 1]]))
+  fpts = points.astype(np.float64) + 0.25
+  fpts[:, 2] = points[:, 2]
+  np.testing.assert_allclose(warp.warp_points(fpts, coord_map, map_box, 10),
+                             fpts + np.array([[10, 0, 0], [0, 20, 0]]))
+
+
+def test_mask_irregular_lives_in_map_utils():
+  from sofima_b200.processor import mesh as pmesh
+  assert pmesh.mask_irregular is map_utils.mask_irregular
+  cmap = np.zeros((2, 6, 7), np.float32)
+  cmap[0, 2, 3] = -35.0  # node pushed far to the left: the link to it is folded
+  bad = map_utils.mask_irregular(cmap, (40.0, 40.0), 0.5, dilation_iters=0)
+  assert bad[2, 2] and bad.sum() >= 1 and np.isnan(cmap[0, 2, 2])

@@ -107,3 +107,7 @@ def test_remap_equals_opencv(kind):
   c1, _ = cv.convertMaps(dx, dy, dstmap1type=cv.CV_16SC2, nninterpolation=True)
   np.testing.assert_array_equal(wo.remap(labels, c1, None, 'nearest'),
                                 cv.remap(labels, c1, None, interpolation=cv.INTER_NEAREST))
+
+
+def test_oracle_passes_the_reference_kats():
+  wo.check_reference_kats(wo.warp_subvolume)

@@ -237,3 +237,9 @@ def test_stitch_and_render_3d_tiles(warp):
   # (the last row / column of outer tiles carries no weight with a margin: reference quirk)
   assert np.abs(d2[0, :, :179, :179]).max() <= 1
   Renderer.reset_cache()
+
+
+def test_reference_kats(warp):
+  """The reference's own warp_subvolume tests (tests/warp_test.py:27-78): label translation
+  with ids beyond int32 and a 45-degree rotation of a rhombus (Lanczos default)."""
+  wo.check_reference_kats(warp.warp_subvolume, compat.BoundingBox)
