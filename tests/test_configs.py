@@ -95,3 +95,14 @@ def test_registered_defaults_and_mesh_pipeline():
   d = mp.to_dict()
   assert d['cross_block_config']['integration_config']['stride'] == [320, 320]
   assert dataclasses.is_dataclass(flow_config.default_em_2d().estimate_flow)
+
+
+def test_warp_pipeline_default_em_2d():   # pipeline/warp_config.py:35-50
+  from sofima_b200.pipeline import warp_config
+  t = cfg_lib.DefaultConfigType.EM_2D
+  wp = cfg_lib.default_config(warp_config.WarpPipelineConfig, t)
+  assert wp == warp_config.default_em_2d() and wp.warp == em_2d.warp_config()
+  wp2 = warp_config.default_em_2d({'warp': {'interpolation': 'lanczos', 'data_volinfo': 'd'}})
+  assert wp2.warp.interpolation == 'lanczos' and wp2.warp.data_volinfo == 'd'
+  assert wp2.warp.stride == wp.warp.stride
+  assert wp.to_dict()['warp']['stride'] == 40

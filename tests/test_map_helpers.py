@@ -2,6 +2,7 @@
 known-answer tests (tests/map_utils_test.py:93-127, 155-168)."""
 
 import numpy as np
+import pytest
 
 from sofima_b200 import compat
 from sofima_b200 import map_utils
@@ -197,3 +198,43 @@ def test_mask_irregular_lives_in_map_utils():
   cmap[0, 2, 3] = -35.0  # node pushed far to the left: the link to it is folded
   bad = map_utils.mask_irregular(cmap, (40.0, 40.0), 0.5, dilation_iters=0)
   assert bad[2, 2] and bad.sum() >= 1 and np.isnan(cmap[0, 2, 2])
+
+
+def test_map_processors():
+  """processor/maps.py:332-498 -- InvertMap, ResampleMap, MaskIrregularities, FillMissing."""
+  from sofima_b200.processor import maps
+  box = compat.BoundingBox(start=(10, 20, 3), size=(30, 30, 1))
+  _, hx = np.mgrid[:30, :30]
+  cmap = np.zeros([2, 1, 30, 30], np.float32)
+  cmap[1, 0] = np.sin(hx / 15) * 10
+  vol = np.zeros((2, 8, 100, 100), np.float32)
+  inv = maps.InvertMap(maps.InvertMap.Config(stride=40.0, crop_output=False), vol)
+  (out,) = inv.process(compat.Subvolume(cmap, box))
+  assert out.bbox == box
+  np.testing.assert_array_almost_equal(out.data[:, :, 1:, 1:], -cmap[:, :, 1:, 1:], decimal=4)
+  cropped = maps.InvertMap(maps.InvertMap.Config(stride=40.0), vol).process(
+      compat.Subvolume(cmap, box))[0]
+  assert cropped.bbox == map_utils.inner_box(cmap.astype(np.float64), box, 40.0)
+  assert maps.InvertMap(maps.InvertMap.Config(stride=40.0), vol).process(
+      compat.Subvolume(np.full_like(cmap, np.nan), box)) == []
+  with pytest.raises(ValueError):
+    maps.InvertMap(maps.InvertMap.Config(stride=40.0))
+  # ResampleMap: twice the node density, values follow the smooth field
+  rs = maps.ResampleMap(maps.ResampleMap.Config(stride=40, out_stride=20))
+  (fine,) = rs.process(compat.Subvolume(cmap, box))
+  assert fine.bbox == box.scale([2, 2, 1.0]) and fine.data.shape == (2, 1, 60, 60)
+  np.testing.assert_allclose(fine.data[1, 0, ::2, ::2][:29, :29], cmap[1, 0, :29, :29], atol=1e-6)
+  np.testing.assert_allclose(rs.pixelsize(np.array([8.0, 8.0, 30.0])), [4.0, 4.0, 30.0])
+  # MaskIrregularities: 3 nodes of context are cropped, a folded node is masked with its ring
+  mi = maps.MaskIrregularities((40.0, 40.0), 0.5)
+  bad = np.zeros([2, 1, 30, 30], np.float32)
+  bad[0, 0, 15, 15] = -35
+  got = mi.process(compat.Subvolume(bad, box))
+  assert got.data.shape == (2, 1, 24, 24) and np.isnan(got.data[0, 0, 12, 12])
+  assert np.isnan(got.data).sum() >= 2 and np.isfinite(got.data[0, 0, 0, 0])
+  # FillMissing
+  holes = cmap.copy()
+  holes[:, 0, 10:12, 10:12] = np.nan
+  filled = maps.FillMissing().process(compat.Subvolume(holes, box))
+  assert np.isfinite(filled.data).all()
+  np.testing.assert_allclose(filled.data, cmap, atol=0.05)
