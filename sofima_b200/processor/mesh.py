@@ -28,6 +28,7 @@ from scipy import ndimage
 from .. import compat
 from .. import map_utils
 from .. import mesh as mesh_lib
+from . import client_utils
 
 Subvolume = compat.Subvolume
 
@@ -54,11 +55,7 @@ def apply_mask(flow: np.ndarray, mask: np.ndarray):
 mask_irregular = map_utils.mask_irregular
 
 
-def get_block_id(z: int, starts: Sequence[int], backward: bool) -> int:
-  """Block number of section `z` (processor/client_utils.py:22-27)."""
-  if backward:
-    return bisect.bisect_left(starts, z)
-  return bisect.bisect_right(starts, z)
+get_block_id = client_utils.get_block_id  # reference: processor/client_utils.py
 
 
 @dataclasses.dataclass(frozen=True)

@@ -282,3 +282,14 @@ def test_optim_flow_decorator_geometry():
     decorators.OptimFlow(fixed_spec=img, image_dims=('x', 'y')).decorate(vol)
   with pytest.raises(ValueError):
     decorators.OptimFlow(fixed_spec=vol, image_dims=('x',)).decorate(vol)
+
+
+def test_get_block_id():  # tests/client_utils_test.py:24-40
+  from sofima_b200.processor import client_utils
+  from sofima_b200.processor import mesh as pmesh
+  assert pmesh.get_block_id is client_utils.get_block_id
+  fwd_starts = [0, 50, 100, 150, 200]  # blocks 0..49, 50..99, ...
+  assert [client_utils.get_block_id(z, fwd_starts, False) for z in (10, 0, 49, 50)] == [1, 1, 1, 2]
+  bwd_starts = [50, 100, 150, 200]  # blocks 0..50, 51..100, ...
+  assert [client_utils.get_block_id(z, bwd_starts, True)
+          for z in (10, 0, 50, 51, 100)] == [0, 0, 0, 1, 1]
